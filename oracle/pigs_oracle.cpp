@@ -364,6 +364,16 @@ struct orc_sim {
         return accept;
     }
 
+    /* int(n*grnd()) as written at every site of Appendix A.  grnd() is [0,1] INCLUSIVE
+     * (Q6): u == 1 (p = 2^-32 per draw) indexes one past the range in the reference,
+     * which is an out-of-bounds access there; the oracle (and the CUDA path, identically)
+     * clamps that single case so long baseline runs cannot corrupt memory. */
+    inline int draw_int(int n) {
+        int v = (int)(n * rng.grnd());
+        if (v >= n) v = n > 0 ? n - 1 : 0;
+        return v;
+    }
+
     /* ---- bridge primitives: identical text instantiated ~20 times in vpi_mod.f90 ---- */
     /* xprev(k) = Path(k,ip,iprev)-xold(k); wrap; xprev = xold+xprev   (e.g. vpi_mod.f90:517-522) */
     inline double unwrap_prev(int k, double xold, double pprev) const {
@@ -525,7 +535,7 @@ struct orc_sim {
     /* vpi_mod.f90:480-578 */
     void Staging(int Ls, int ip, int& accepted) {
         std::vector<double> OldChain;
-        int ii = (int)((2 * Nb - Ls + 1) * rng.grnd());
+        int ii = draw_int(2 * Nb - Ls + 1);
         int ie = ii + Ls;
         save_chain(OldChain, ip, ii, ie);
         double SumDeltaS = 0.0;
@@ -536,7 +546,7 @@ struct orc_sim {
     /* vpi_mod.f90:582-720 */
     void MoveHead(int Lmax, int ip, int& accepted) {
         std::vector<double> OldChain;
-        int Ls = (int)((Lmax - 1) * rng.grnd()) + 2;
+        int Ls = draw_int(Lmax - 1) + 2;
         int ii = 0, ie = ii + Ls;
         save_chain(OldChain, ip, ii, ie);
         double SumDeltaS = 0.0;
@@ -548,7 +558,7 @@ struct orc_sim {
     /* vpi_mod.f90:724-860 */
     void MoveTail(int Lmax, int ip, int& accepted) {
         std::vector<double> OldChain;
-        int Ls = (int)((Lmax - 1) * rng.grnd()) + 2;
+        int Ls = draw_int(Lmax - 1) + 2;
         int ii = 2 * Nb - Ls, ie = 2 * Nb;
         save_chain(OldChain, ip, ii, ie);
         double SumDeltaS = 0.0;
@@ -561,7 +571,7 @@ struct orc_sim {
     void Bisection(int level, int ip, int& accepted) {
         std::vector<double> OldChain;
         int Nl = level;
-        int ii = (int)((2 * Nb - (1 << Nl) + 1) * rng.grnd());
+        int ii = draw_int(2 * Nb - (1 << Nl) + 1);
         int ie = ii + (1 << Nl);
         save_chain(OldChain, ip, ii, ie);
         bool accept = bisect_levels(ip, ii, Nl);
@@ -571,7 +581,7 @@ struct orc_sim {
     /* vpi_mod.f90:1002-1184 */
     void MoveHeadBisection(int level, int ip, int& accepted) {
         std::vector<double> OldChain;
-        int Nl = (int)((level - 1) * rng.grnd()) + 2;
+        int Nl = draw_int(level - 1) + 2;
         int ii = 0, ie = ii + (1 << Nl);
         save_chain(OldChain, ip, ii, ie);
         double DeltaS = free_end_next(ip, ii, ie, std::sqrt((double)(1 << Nl) * dt));
@@ -585,7 +595,7 @@ struct orc_sim {
     /* vpi_mod.f90:1188-1372 */
     void MoveTailBisection(int level, int ip, int& accepted) {
         std::vector<double> OldChain;
-        int Nl = (int)((level - 1) * rng.grnd()) + 2;
+        int Nl = draw_int(level - 1) + 2;
         int ii = 2 * Nb - (1 << Nl), ie = 2 * Nb;
         save_chain(OldChain, ip, ii, ie);
         double DeltaS = free_end_prev(ip, ie, ii, std::sqrt((double)(1 << Nl) * dt));
@@ -601,8 +611,8 @@ struct orc_sim {
         std::vector<double> OldChain;
         for (int k = 1; k <= dim; ++k) P(k, ip, Nb) = xend[half - 1][k - 1];
         int ii, ie;
-        if (half == 1) { ii = (int)((Nb - Ls + 1) * rng.grnd()); ie = ii + Ls; }
-        else { ii = (int)((Nb - Ls + 1) * rng.grnd()) + Nb; ie = ii + Ls; }
+        if (half == 1) { ii = draw_int(Nb - Ls + 1); ie = ii + Ls; }
+        else { ii = draw_int(Nb - Ls + 1) + Nb; ie = ii + Ls; }
         save_chain(OldChain, ip, ii, ie);
         double SumDeltaS = 0.0;
         for (int j = 1; j <= Ls - 1; ++j) SumDeltaS = SumDeltaS + stage_bead(ip, ii, Ls, j, ie);
@@ -616,7 +626,7 @@ struct orc_sim {
     /* vpi_mod.f90:1495-1656 */
     void MoveHeadHalfChain(int half, int Lmax, int ip, int& accepted) {
         std::vector<double> OldChain;
-        int Ls = (int)((Lmax - 1) * rng.grnd()) + 2;
+        int Ls = draw_int(Lmax - 1) + 2;
         for (int k = 1; k <= dim; ++k) P(k, ip, Nb) = xend[half - 1][k - 1];
         int ii, ie;
         if (half == 1) { ii = 0; ie = ii + Ls; } else { ii = Nb; ie = ii + Ls; }
@@ -636,7 +646,7 @@ struct orc_sim {
     /* vpi_mod.f90:1660-1817 */
     void MoveTailHalfChain(int half, int Lmax, int ip, int& accepted) {
         std::vector<double> OldChain;
-        int Ls = (int)((Lmax - 1) * rng.grnd()) + 2;
+        int Ls = draw_int(Lmax - 1) + 2;
         for (int k = 1; k <= dim; ++k) P(k, ip, Nb) = xend[half - 1][k - 1];
         int ii, ie;
         if (half == 1) { ii = Nb - Ls; ie = Nb; } else { ii = 2 * Nb - Ls; ie = 2 * Nb; }
@@ -663,8 +673,9 @@ struct orc_sim {
     /* vpi_mod.f90:1821-2076 */
     void OpenChain(int Lmax, int ip, int& accepted) {
         std::vector<double> OldChain;
-        int Ls = 2 * (int)(((Lmax - 2) / 2) * rng.grnd()) + 2;
+        int Ls = 2 * draw_int((Lmax - 2) / 2) + 2;
         int half = (int)(rng.grnd() * 2) + 1;
+        if (half > 2) half = 2;
         double SumDeltaS = -std::log(CWorm * density);
         double DeltaS, DeltaK;
         int ii, ie;
@@ -705,8 +716,9 @@ struct orc_sim {
     /* vpi_mod.f90:2080-2266 */
     void CloseChain(int Lmax, int ip, int& accepted) {
         std::vector<double> OldChain;
-        int Ls = 2 * (int)(((Lmax - 2) / 2) * rng.grnd()) + 2;
+        int Ls = 2 * draw_int((Lmax - 2) / 2) + 2;
         int half = (int)(rng.grnd() * 2) + 1;
+        if (half > 2) half = 2;
         double SumDeltaS = std::log(CWorm * density);
         double DeltaS, xnew[3], xold[3];
         int ii, ie;
@@ -753,7 +765,7 @@ struct orc_sim {
         std::vector<double> Pp((size_t)Np, 0.0), OldChain((size_t)dim * (2 * Nb + 1)), OldWorm((size_t)dim * (2 * Nb + 1));
         double xij[3], rij2, Sk, Sw, uran, sum;
         swap_acc = false;
-        int Ls = 2 * (int)(((Lmax - 2) / 2) * rng.grnd()) + 2;
+        int Ls = 2 * draw_int((Lmax - 2) / 2) + 2;
         int ii = Nb - Ls, ie = Nb;
         int ikl = 0;
         Sw = 0.0;
@@ -1013,8 +1025,7 @@ struct orc_sim {
                 }
             } else {
                 if (iupdate == 1) {
-                    iworm = (int)(rng.grnd() * Np) + 1;
-                    if (iworm > Np) iworm = Np;         /* Q6: u==1 (p=2^-32) would index Np+1 in the reference */
+                    iworm = draw_int(Np) + 1;           /* int(grnd()*Np)+1, vpi.f90:315 */
                     OpenChain(Lstag, iworm, acc_open);
                     b.try_open = b.try_open + 1;
                     PermutationSampling(iworm, false, 0, false);

@@ -1,0 +1,624 @@
+// pigs_capi.cu -- the C ABI of libpigs_cuda (include/pigs_cuda.h): context,
+// state transfer, launch policy.  No torch types, no CPU fallback.
+#include "../../include/pigs_cuda.h"
+#include "pigs_launch.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pigs;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& m) { g_err = m; return code; }
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(PIGS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+struct pigs_ctx {
+    pigs_params hp;
+    DevParams P;
+    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32;
+    size_t smem = 0;
+    int nvec = 0;
+    bool tables_set = false;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    long long launches = 0;
+    // device buffers
+    double *d_logwf = nullptr, *d_vtab = nullptr, *d_path = nullptr, *d_xend = nullptr, *d_acc = nullptr, *d_vec = nullptr;
+    double* d_stage = nullptr;      // AoS staging for state transfer
+    int *d_istate = nullptr, *d_cyc = nullptr, *d_hist = nullptr, *d_iout = nullptr;
+    unsigned* d_mt = nullptr;
+    unsigned long long* d_pctr = nullptr;
+    long long* d_cnt = nullptr;
+    size_t stage_doubles = 0;
+};
+
+extern "C" const char* pigs_last_error(void) { return g_err.c_str(); }
+extern "C" int pigs_version(void) { return 100; }
+
+static SweepArgs base_args(pigs_ctx* h) {
+    SweepArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.chain_only = -1;
+    A.groups_per_cta = h->G;
+    A.threads_per_chain = h->T;
+    A.var = h->var;
+    return A;
+}
+static int launch(pigs_ctx* h, const SweepArgs& A) {
+    CK(launch_sweep(h->mt, h->var, h->P, A, h->grid, h->block, h->smem, h->st));
+    h->launches += 1;
+    return PIGS_OK;
+}
+
+// launch policy: threads per chain T, chain groups per CTA G, table placement.
+static int plan(pigs_ctx* h) {
+    const pigs_params& p = h->hp;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, p.device));
+    const int nsm = prop.multiProcessorCount;
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    int T = p.threads_per_chain;
+    if (T == 0) {
+        // fill ~32 warps per SM: few chains -> wide groups, many chains -> one warp each
+        long long want = (long long)nsm * 1024 / (p.n_chains > 0 ? p.n_chains : 1);
+        T = 32;
+        while (T * 2 <= want && T < 256) T *= 2;
+    }
+    if (T != 32 && T != 64 && T != 128 && T != 256 && T != 512) return fail(PIGS_E_ARG, "threads_per_chain must be 0,32,64,128,256,512");
+    const size_t gbytes = grp_smem_doubles(h->P.S, h->P.Np, T / 32) * sizeof(double);
+    const size_t tabbytes = (size_t)(p.Nmax + 2) * sizeof(double);
+    int Gmax = 1024 / T;
+    if (T > 32 && Gmax > 16) Gmax = 16;        // named barriers 0..15
+    int Gneed = (p.n_chains + nsm - 1) / nsm;  // chains per SM if spread evenly
+    if (Gneed < 1) Gneed = 1;
+    int var;
+    if (p.trap) var = 3;
+    else {
+        int tm = p.table_mode;
+        if (tm < 0) {
+            // both tables in shared memory when at least min(Gneed,4) groups still fit beside them
+            int gmin = Gneed < 4 ? Gneed : 4;
+            if (2 * tabbytes + gmin * gbytes <= smem_max) tm = 2;
+            else if (tabbytes + gmin * gbytes <= smem_max) tm = 1;
+            else tm = 0;
+        }
+        if (tm < 0 || tm > 2) return fail(PIGS_E_ARG, "table_mode must be -1,0,1,2");
+        var = tm;
+    }
+    const size_t fixed = (var == 1 ? tabbytes : (var == 2 ? 2 * tabbytes : 0));
+    if (fixed + gbytes > smem_max) return fail(PIGS_E_ARG, "configuration does not fit in shared memory; lower table_mode");
+    int G = (int)((smem_max - fixed) / gbytes);
+    if (G > Gmax) G = Gmax;
+    if (G > Gneed) G = Gneed;
+    if (G < 1) G = 1;
+    h->T = T; h->G = G; h->var = var; h->block = T * G;
+    h->smem = fixed + (size_t)G * gbytes;
+    CK(sweep_set_smem(h->mt, var, h->smem));
+    int per_sm = 1;
+    CK(sweep_occupancy(h->mt, var, h->block, h->smem, &per_sm));
+    if (per_sm < 1) return fail(PIGS_E_CUDA, "sweep kernel cannot be resident with this configuration");
+    int ctas = (p.n_chains + G - 1) / G;
+    int cap = nsm * per_sm;
+    h->grid = ctas < cap ? ctas : cap;
+    return PIGS_OK;
+}
+
+extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
+    if (!p || !out) return fail(PIGS_E_ARG, "null argument");
+    *out = nullptr;
+    if (p->dim < 1 || p->dim > 3) return fail(PIGS_E_ARG, "dim must be 1..3");
+    if (p->Np < 2 || p->Nb < 1 || p->Nmax < 4 || p->n_chains < 1) return fail(PIGS_E_ARG, "Np>=2, Nb>=1, Nmax>=4, n_chains>=1 required");
+    if (p->Nbin < 1 || p->Nk < 0 || p->Npw < 0) return fail(PIGS_E_ARG, "bad Nbin/Nk/Npw");
+    if (p->sampling != 0 && p->sampling != 1) return fail(PIGS_E_ARG, "sampling must be 0 ('sta') or 1 ('bis')");
+    if (p->CMFreq < 1 || p->Nstag < 0 || p->Nobdm < 0) return fail(PIGS_E_ARG, "bad CMFreq/Nstag/Nobdm");
+    // constraints implied by the reference's index arithmetic
+    if (p->sampling == 1) {
+        int lv = p->Nlev < 2 ? 2 : p->Nlev;     // head/tail bisection draw Nlev' in [2, max(2,Nlev)]
+        if ((1 << lv) > 2 * p->Nb) return fail(PIGS_E_ARG, "2**Nlev must not exceed 2*Nb");
+    } else if (p->Lstag < 2 || p->Lstag > 2 * p->Nb) return fail(PIGS_E_ARG, "2 <= Lstag <= 2*Nb required");
+    if ((p->Nobdm > 0 || p->CWorm > 0 || p->swapping) && (p->Lstag < 2 || p->Lstag > p->Nb))
+        return fail(PIGS_E_ARG, "worm moves need 2 <= Lstag <= Nb");
+    if (p->Lstag < 2) return fail(PIGS_E_ARG, "Lstag >= 2 required (OpenChain is attempted even when CWorm = 0)");
+    if (p->Lstag > p->Nb) return fail(PIGS_E_ARG, "Lstag <= Nb required (OpenChain is attempted even when CWorm = 0)");
+    if (p->rng_mode != PIGS_RNG_PHILOX && p->rng_mode != PIGS_RNG_MT_REPLAY) return fail(PIGS_E_ARG, "bad rng_mode");
+    if (!(p->dt > 0) || !(p->dr > 0) || !(p->rcut > 0)) return fail(PIGS_E_ARG, "dt, dr, rcut must be positive");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PIGS_E_CUDA, std::string("no CUDA device: libpigs_cuda has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    if (p->device < 0 || p->device >= ndev) return fail(PIGS_E_ARG, "bad device ordinal");
+    CK(cudaSetDevice(p->device));
+
+    pigs_ctx* h = new pigs_ctx();
+    h->hp = *p;
+    h->mt = p->rng_mode == PIGS_RNG_MT_REPLAY ? 1 : 0;
+    DevParams& P = h->P;
+    std::memset(&P, 0, sizeof P);
+    P.dim = p->dim; P.Np = p->Np; P.Nb = p->Nb; P.S = 2 * p->Nb + 1;
+    P.NpS = (p->Np + 3) & ~3;                 // 32-byte aligned component rows
+    P.Nmax = p->Nmax; P.Nbin = p->Nbin; P.Nk = p->Nk; P.Npw = p->Npw;
+    P.trap = p->trap != 0; P.sampling = p->sampling; P.Lstag = p->Lstag; P.Nlev = p->Nlev; P.Nstag = p->Nstag;
+    P.Nobdm = p->Nobdm; P.swapping = p->swapping != 0; P.CMFreq = p->CMFreq; P.n_chains = p->n_chains;
+    for (int k = 0; k < 3; ++k) {
+        bool used = k < p->dim && !p->trap;
+        P.L[k] = used ? p->Lbox[k] : 1e300;
+        P.Lh[k] = used ? 0.5 * p->Lbox[k] : 0.5e300;          // LboxHalf, vpi.f90:118
+        P.qbin[k] = used ? 2.0 * std::acos(-1.0) / p->Lbox[k] : 0.0;   // vpi.f90:119
+        P.a_ho[k] = k < p->dim ? p->a_ho[k] : 1.0;
+    }
+    P.rcut2 = p->rcut * p->rcut;              // vpi.f90:127
+    P.dr = p->dr; P.inv_dr = 1.0 / p->dr;
+    P.rbin = p->rcut / (double)(float)p->Nbin;   // vpi.f90:128
+    P.dt = p->dt; P.delta_cm = p->delta_cm; P.CWorm = p->CWorm; P.density = p->density;
+    P.pi = std::acos(-1.0);
+    P.logCd = std::log(p->CWorm * p->density);   // -inf when CWorm = 0: every open attempt is rejected (F8)
+    P.seed = p->seed;
+    P.chain_stride = (size_t)P.S * 3 * P.NpS;
+    P.off_gr = NE; P.off_sk = P.off_gr + P.Nbin; P.off_nr = P.off_sk + P.dim * P.Nk;
+    P.nacc = P.off_nr + P.Nbin * (P.Npw + 1);
+    h->nvec = NE + NCNT + (P.nacc - NE);
+
+    const size_t nc = (size_t)p->n_chains;
+#define ALLOC(ptr, count) CK(cudaMalloc((void**)&(ptr), sizeof(*(ptr)) * (count)))
+    ALLOC(h->d_logwf, p->Nmax + 2); ALLOC(h->d_vtab, p->Nmax + 2);
+    ALLOC(h->d_path, nc * P.chain_stride); ALLOC(h->d_xend, nc * 6);
+    ALLOC(h->d_istate, nc * IS_N); ALLOC(h->d_cyc, nc * P.Np); ALLOC(h->d_hist, nc * P.Np);
+    ALLOC(h->d_mt, nc * 624); ALLOC(h->d_pctr, nc); ALLOC(h->d_acc, nc * P.nacc); ALLOC(h->d_cnt, nc * NCNT);
+    ALLOC(h->d_vec, h->nvec); ALLOC(h->d_iout, nc * 2);
+#undef ALLOC
+    CK(cudaMemset(h->d_path, 0, sizeof(double) * nc * P.chain_stride));
+    CK(cudaMemset(h->d_xend, 0, sizeof(double) * nc * 6));
+    CK(cudaMemset(h->d_istate, 0, sizeof(int) * nc * IS_N));
+    CK(cudaMemset(h->d_cyc, 0, sizeof(int) * nc * P.Np));
+    CK(cudaMemset(h->d_hist, 0, sizeof(int) * nc * P.Np));
+    CK(cudaMemset(h->d_pctr, 0, sizeof(unsigned long long) * nc));
+    CK(cudaMemset(h->d_acc, 0, sizeof(double) * nc * P.nacc));
+    CK(cudaMemset(h->d_cnt, 0, sizeof(long long) * nc * NCNT));
+    CK(cudaMemset(h->d_logwf, 0, sizeof(double) * (p->Nmax + 2)));
+    CK(cudaMemset(h->d_vtab, 0, sizeof(double) * (p->Nmax + 2)));
+    P.logwf = h->d_logwf; P.vtab = h->d_vtab; P.path = h->d_path; P.xend = h->d_xend; P.istate = h->d_istate;
+    P.cyc = h->d_cyc; P.hist = h->d_hist; P.mt = h->d_mt; P.pctr = h->d_pctr; P.acc = h->d_acc; P.cnt = h->d_cnt;
+    CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+    int rc = plan(h);
+    if (rc != PIGS_OK) { pigs_destroy(h); return rc; }
+    // sgrnd(seed + chain) for every chain (random_mod.f90:5-31)
+    *out = h;
+    rc = pigs_sgrnd(h, -1, (int32_t)p->seed);
+    if (rc != PIGS_OK) { *out = nullptr; pigs_destroy(h); return rc; }
+    return PIGS_OK;
+}
+
+extern "C" int pigs_destroy(pigs_handle h) {
+    if (!h) return PIGS_OK;
+    cudaSetDevice(h->hp.device);
+    cudaFree(h->d_logwf); cudaFree(h->d_vtab); cudaFree(h->d_path); cudaFree(h->d_xend); cudaFree(h->d_istate);
+    cudaFree(h->d_cyc); cudaFree(h->d_hist); cudaFree(h->d_mt); cudaFree(h->d_pctr); cudaFree(h->d_acc);
+    cudaFree(h->d_cnt); cudaFree(h->d_vec); cudaFree(h->d_iout); cudaFree(h->d_stage);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return PIGS_OK;
+}
+
+#define NEED(h) do { if (!(h)) return fail(PIGS_E_ARG, "null handle"); CK(cudaSetDevice((h)->hp.device)); } while (0)
+#define NEED_CHAIN(h, c) do { if ((c) < 0 || (c) >= (h)->hp.n_chains) return fail(PIGS_E_ARG, "chain index out of range"); } while (0)
+
+static int ensure_stage(pigs_ctx* h, size_t doubles) {
+    if (h->stage_doubles >= doubles) return PIGS_OK;
+    if (h->d_stage) CK(cudaFree(h->d_stage));
+    h->d_stage = nullptr; h->stage_doubles = 0;
+    CK(cudaMalloc((void**)&h->d_stage, doubles * sizeof(double)));
+    h->stage_doubles = doubles;
+    return PIGS_OK;
+}
+
+extern "C" int pigs_set_tables(pigs_handle h, const double* LogWF, const double* VTable) {
+    NEED(h);
+    if (!LogWF || !VTable) return fail(PIGS_E_ARG, "null table");
+    size_t n = sizeof(double) * (h->hp.Nmax + 2);
+    CK(cudaMemcpyAsync(h->d_logwf, LogWF, n, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->d_vtab, VTable, n, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->tables_set = true;
+    return PIGS_OK;
+}
+
+// ---- state transfer ---------------------------------------------------------------------------
+static int put_paths(pigs_ctx* h, int chain0, int nchain, const double* Path) {
+    const DevParams& P = h->P;
+    size_t per = (size_t)P.S * P.Np * P.dim;
+    int rc = ensure_stage(h, per * nchain);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_stage, Path, per * nchain * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CK(launch_aos_to_soa(P, h->d_stage, h->d_path + (size_t)chain0 * P.chain_stride, nchain, h->st));
+    h->launches += 1;
+    return PIGS_OK;
+}
+static int get_paths(pigs_ctx* h, int chain0, int nchain, double* Path) {
+    const DevParams& P = h->P;
+    size_t per = (size_t)P.S * P.Np * P.dim;
+    int rc = ensure_stage(h, per * nchain);
+    if (rc) return rc;
+    CK(launch_soa_to_aos(P, h->d_path + (size_t)chain0 * P.chain_stride, h->d_stage, nchain, h->st));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(Path, h->d_stage, per * nchain * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    return PIGS_OK;
+}
+static int put_scalars(pigs_ctx* h, int chain0, int nchain, const double* xend, const int32_t* isopen, const int32_t* iworm) {
+    const int dim = h->P.dim;
+    std::vector<double> xe((size_t)nchain * 6, 0.0);
+    for (int c = 0; c < nchain; ++c) for (int j = 0; j < 2; ++j) for (int k = 0; k < dim; ++k) xe[(size_t)c * 6 + j * 3 + k] = xend[((size_t)c * 2 + j) * dim + k];
+    CK(cudaMemcpyAsync(h->d_xend + (size_t)chain0 * 6, xe.data(), xe.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    std::vector<int> ist((size_t)nchain * IS_N);
+    CK(cudaMemcpyAsync(ist.data(), h->d_istate + (size_t)chain0 * IS_N, ist.size() * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    for (int c = 0; c < nchain; ++c) { ist[(size_t)c * IS_N + IS_OPEN] = isopen[c] != 0; ist[(size_t)c * IS_N + IS_IWORM] = iworm[c]; }
+    CK(cudaMemcpyAsync(h->d_istate + (size_t)chain0 * IS_N, ist.data(), ist.size() * sizeof(int), cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return PIGS_OK;
+}
+static int get_scalars(pigs_ctx* h, int chain0, int nchain, double* xend, int32_t* isopen, int32_t* iworm) {
+    const int dim = h->P.dim;
+    std::vector<double> xe((size_t)nchain * 6);
+    std::vector<int> ist((size_t)nchain * IS_N);
+    CK(cudaMemcpyAsync(xe.data(), h->d_xend + (size_t)chain0 * 6, xe.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(ist.data(), h->d_istate + (size_t)chain0 * IS_N, ist.size() * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    for (int c = 0; c < nchain; ++c) {
+        if (xend) for (int j = 0; j < 2; ++j) for (int k = 0; k < dim; ++k) xend[((size_t)c * 2 + j) * dim + k] = xe[(size_t)c * 6 + j * 3 + k];
+        if (isopen) isopen[c] = ist[(size_t)c * IS_N + IS_OPEN];
+        if (iworm) iworm[c] = ist[(size_t)c * IS_N + IS_IWORM];
+    }
+    return PIGS_OK;
+}
+
+extern "C" int pigs_set_state(pigs_handle h, int chain, const double* Path, const double* xend, int isopen, int iworm) {
+    NEED(h); NEED_CHAIN(h, chain);
+    if (!Path || !xend) return fail(PIGS_E_ARG, "null state");
+    int rc = put_paths(h, chain, 1, Path);
+    if (rc) return rc;
+    int32_t io = isopen, iw = iworm;
+    return put_scalars(h, chain, 1, xend, &io, &iw);
+}
+extern "C" int pigs_get_state(pigs_handle h, int chain, double* Path, double* xend, int* isopen, int* iworm) {
+    NEED(h); NEED_CHAIN(h, chain);
+    if (Path) { int rc = get_paths(h, chain, 1, Path); if (rc) return rc; }
+    int32_t io = 0, iw = 0;
+    int rc = get_scalars(h, chain, 1, xend, &io, &iw);
+    if (isopen) *isopen = io;
+    if (iworm) *iworm = iw;
+    return rc;
+}
+extern "C" int pigs_set_state_all(pigs_handle h, const double* Path, const double* xend, const int32_t* isopen, const int32_t* iworm) {
+    NEED(h);
+    if (!Path || !xend || !isopen || !iworm) return fail(PIGS_E_ARG, "null state");
+    int rc = put_paths(h, 0, h->hp.n_chains, Path);
+    if (rc) return rc;
+    return put_scalars(h, 0, h->hp.n_chains, xend, isopen, iworm);
+}
+extern "C" int pigs_get_state_all(pigs_handle h, double* Path, double* xend, int32_t* isopen, int32_t* iworm) {
+    NEED(h);
+    if (Path) { int rc = get_paths(h, 0, h->hp.n_chains, Path); if (rc) return rc; }
+    return get_scalars(h, 0, h->hp.n_chains, xend, isopen, iworm);
+}
+
+extern "C" int pigs_get_perm(pigs_handle h, int chain, int* iperm, int32_t* cycle, int32_t* hist, int* new_pc, int* end_pc) {
+    NEED(h); NEED_CHAIN(h, chain);
+    int ist[IS_N];
+    CK(cudaMemcpyAsync(ist, h->d_istate + (size_t)chain * IS_N, sizeof ist, cudaMemcpyDeviceToHost, h->st));
+    if (cycle) CK(cudaMemcpyAsync(cycle, h->d_cyc + (size_t)chain * h->P.Np, sizeof(int) * h->P.Np, cudaMemcpyDeviceToHost, h->st));
+    if (hist) CK(cudaMemcpyAsync(hist, h->d_hist + (size_t)chain * h->P.Np, sizeof(int) * h->P.Np, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (iperm) *iperm = ist[IS_IPERM];
+    if (new_pc) *new_pc = ist[IS_NEWPC];
+    if (end_pc) *end_pc = ist[IS_ENDPC];
+    return PIGS_OK;
+}
+extern "C" int pigs_set_perm(pigs_handle h, int chain, int iperm, const int32_t* cycle, const int32_t* hist, int new_pc, int end_pc) {
+    NEED(h); NEED_CHAIN(h, chain);
+    int ist[IS_N];
+    CK(cudaMemcpyAsync(ist, h->d_istate + (size_t)chain * IS_N, sizeof ist, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    ist[IS_IPERM] = iperm; ist[IS_NEWPC] = new_pc != 0; ist[IS_ENDPC] = end_pc != 0;
+    CK(cudaMemcpyAsync(h->d_istate + (size_t)chain * IS_N, ist, sizeof ist, cudaMemcpyHostToDevice, h->st));
+    if (cycle) CK(cudaMemcpyAsync(h->d_cyc + (size_t)chain * h->P.Np, cycle, sizeof(int) * h->P.Np, cudaMemcpyHostToDevice, h->st));
+    if (hist) CK(cudaMemcpyAsync(h->d_hist + (size_t)chain * h->P.Np, hist, sizeof(int) * h->P.Np, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return PIGS_OK;
+}
+
+// ---- random streams ----------------------------------------------------------------------------
+extern "C" int pigs_sgrnd(pigs_handle h, int chain, int32_t seed) {
+    NEED(h);
+    if (chain >= h->hp.n_chains) return fail(PIGS_E_ARG, "chain index out of range");
+    SweepArgs A = base_args(h);
+    A.op = OP_SEED; A.seed = seed; A.chain_only = chain < 0 ? -1 : chain;
+    int rc = launch(h, A);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->st));
+    return PIGS_OK;
+}
+extern "C" int pigs_get_mt(pigs_handle h, int chain, uint32_t* mt624, int32_t* mti) {
+    NEED(h); NEED_CHAIN(h, chain);
+    int v = 0;
+    if (mt624) CK(cudaMemcpyAsync(mt624, h->d_mt + (size_t)chain * 624, 624 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(&v, h->d_istate + (size_t)chain * IS_N + IS_MTI, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (mti) *mti = v;
+    return PIGS_OK;
+}
+extern "C" int pigs_set_mt(pigs_handle h, int chain, const uint32_t* mt624, int32_t mti) {
+    NEED(h); NEED_CHAIN(h, chain);
+    if (!mt624) return fail(PIGS_E_ARG, "null mt state");
+    int v = mti;
+    CK(cudaMemcpyAsync(h->d_mt + (size_t)chain * 624, mt624, 624 * sizeof(unsigned), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->d_istate + (size_t)chain * IS_N + IS_MTI, &v, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return PIGS_OK;
+}
+static int draws(pigs_ctx* h, int op, int chain, int n, double* out) {
+    if (n < 0 || !out) return fail(PIGS_E_ARG, "bad draw request");
+    if (n == 0) return PIGS_OK;
+    int rc = ensure_stage(h, (size_t)n);
+    if (rc) return rc;
+    SweepArgs A = base_args(h);
+    A.op = op; A.nstep = n; A.chain_only = chain; A.draws = h->d_stage;
+    rc = launch(h, A);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, h->d_stage, sizeof(double) * n, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return PIGS_OK;
+}
+extern "C" int pigs_grnd(pigs_handle h, int chain, int n, double* out) { NEED(h); NEED_CHAIN(h, chain); return draws(h, OP_UNIFORM, chain, n, out); }
+extern "C" int pigs_rangauss(pigs_handle h, int chain, int n, double* out) { NEED(h); NEED_CHAIN(h, chain); return draws(h, OP_GAUSS, chain, n, out); }
+
+// ---- production path ---------------------------------------------------------------------------
+extern "C" int pigs_run_block_async(pigs_handle h, int Nstep) {
+    NEED(h);
+    if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
+    if (Nstep < 0) return fail(PIGS_E_ARG, "Nstep < 0");
+    CK(cudaEventRecord(h->ev0, h->st));
+    CK(launch_zero_block(h->P, h->st));
+    SweepArgs A = base_args(h);
+    A.op = OP_BLOCK; A.nstep = Nstep;
+    int rc = launch(h, A);
+    if (rc) return rc;
+    CK(launch_reduce_block(h->P, h->d_vec, h->st));
+    h->launches += 2;
+    CK(cudaEventRecord(h->ev1, h->st));
+    return PIGS_OK;
+}
+extern "C" int pigs_sync(pigs_handle h) {
+    NEED(h);
+    CK(cudaStreamSynchronize(h->st));
+    return PIGS_OK;
+}
+extern "C" int pigs_run_block(pigs_handle h, int Nstep) {
+    int rc = pigs_run_block_async(h, Nstep);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return PIGS_OK;
+}
+extern "C" int pigs_last_block_ms(pigs_handle h, float* ms) {
+    NEED(h);
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    if (ms) *ms = h->last_ms;
+    return PIGS_OK;
+}
+extern "C" int pigs_stream(pigs_handle h, void** stream) { NEED(h); if (stream) *stream = (void*)h->st; return PIGS_OK; }
+extern "C" int pigs_launch_count(pigs_handle h, int64_t* n) { NEED(h); if (n) *n = h->launches; return PIGS_OK; }
+
+static void unpack(const pigs_ctx* h, const double* vec, pigs_block_result* out, double* gr, double* Sk, double* nrho) {
+    const DevParams& P = h->P;
+    if (out) {
+        double* e = &out->sumE;
+        for (int i = 0; i < NE; ++i) e[i] = vec[i];
+        int64_t* c = &out->idiag_block;
+        for (int i = 0; i < NCNT; ++i) c[i] = (int64_t)llround(vec[NE + i]);
+    }
+    const double* hst = vec + NE + NCNT;
+    if (gr) std::memcpy(gr, hst, sizeof(double) * P.Nbin);
+    if (Sk) std::memcpy(Sk, hst + P.Nbin, sizeof(double) * P.dim * P.Nk);
+    if (nrho) std::memcpy(nrho, hst + P.Nbin + P.dim * P.Nk, sizeof(double) * P.Nbin * (P.Npw + 1));
+}
+extern "C" int pigs_get_block(pigs_handle h, pigs_block_result* out, double* gr, double* Sk, double* nrho) {
+    NEED(h);
+    std::vector<double> v((size_t)h->nvec);
+    CK(cudaMemcpyAsync(v.data(), h->d_vec, sizeof(double) * h->nvec, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    unpack(h, v.data(), out, gr, Sk, nrho);
+    return PIGS_OK;
+}
+extern "C" int pigs_get_block_chain(pigs_handle h, int chain, pigs_block_result* out, double* gr, double* Sk, double* nrho) {
+    NEED(h); NEED_CHAIN(h, chain);
+    const DevParams& P = h->P;
+    std::vector<double> a((size_t)P.nacc), v((size_t)h->nvec);
+    std::vector<long long> c(NCNT);
+    CK(cudaMemcpyAsync(a.data(), h->d_acc + (size_t)chain * P.nacc, sizeof(double) * P.nacc, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(c.data(), h->d_cnt + (size_t)chain * NCNT, sizeof(long long) * NCNT, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    for (int i = 0; i < NE; ++i) v[i] = a[i];
+    for (int i = 0; i < NCNT; ++i) v[NE + i] = (double)c[i];
+    for (int i = NE; i < P.nacc; ++i) v[NCNT + i] = a[i];
+    unpack(h, v.data(), out, gr, Sk, nrho);
+    return PIGS_OK;
+}
+extern "C" int pigs_block_vector(pigs_handle h, double** dev_ptr, int* n) {
+    NEED(h);
+    if (dev_ptr) *dev_ptr = h->d_vec;
+    if (n) *n = h->nvec;
+    return PIGS_OK;
+}
+extern "C" int pigs_unpack_block_vector(pigs_handle h, const double* vec, pigs_block_result* out, double* gr, double* Sk, double* nrho) {
+    if (!h || !vec) return fail(PIGS_E_ARG, "null argument");
+    unpack(h, vec, out, gr, Sk, nrho);
+    return PIGS_OK;
+}
+
+// ---- unit API ----------------------------------------------------------------------------------
+extern "C" int pigs_move(pigs_handle h, int move, int ip, int half, int32_t* accepted, int32_t* aux) {
+    NEED(h);
+    if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
+    if (move < 0 || move > 13) return fail(PIGS_E_ARG, "unknown move");
+    if (ip < 1 || ip > h->hp.Np) return fail(PIGS_E_ARG, "ip out of range");
+    if (move >= 7 && move <= 10 && half != 1 && half != 2) return fail(PIGS_E_ARG, "half must be 1 or 2");
+    SweepArgs A = base_args(h);
+    A.op = OP_MOVE; A.move = move; A.ip0 = ip - 1; A.half = half;
+    A.accepted = h->d_iout; A.aux = h->d_iout + h->hp.n_chains;
+    int rc = launch(h, A);
+    if (rc) return rc;
+    if (accepted) CK(cudaMemcpyAsync(accepted, h->d_iout, sizeof(int) * h->hp.n_chains, cudaMemcpyDeviceToHost, h->st));
+    if (aux) CK(cudaMemcpyAsync(aux, h->d_iout + h->hp.n_chains, sizeof(int) * h->hp.n_chains, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return PIGS_OK;
+}
+
+// host AoS [n][Np][dim] -> device SoA [n][3][NpS] (unit calls are test-sized; transposed on the host)
+static void to_soa(const DevParams& P, long long nslice, const double* aos, std::vector<double>& soa) {
+    soa.assign((size_t)nslice * 3 * P.NpS, 0.0);
+    for (long long s = 0; s < nslice; ++s)
+        for (int ip = 0; ip < P.Np; ++ip)
+            for (int k = 0; k < P.dim; ++k) soa[((size_t)s * 3 + k) * P.NpS + ip] = aos[((size_t)s * P.Np + ip) * P.dim + k];
+}
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+extern "C" int pigs_update_action(pigs_handle h, int n, const double* R, const int32_t* ip, const int32_t* ib,
+                                  const double* xnew, const double* xold, double* DeltaS) {
+    NEED(h);
+    if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
+    if (n < 0 || !R || !ip || !ib || !xnew || !xold || !DeltaS) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;
+    const DevParams& P = h->P;
+    for (int i = 0; i < n; ++i)
+        if (ip[i] < 1 || ip[i] > P.Np || ib[i] < 0 || ib[i] > 2 * P.Nb) return fail(PIGS_E_ARG, "ip/ib out of range");
+    std::vector<double> soa;
+    to_soa(P, n, R, soa);
+    DevBuf dR, dip, dib, dxn, dxo, dS;
+    CK(cudaMalloc(&dR.p, soa.size() * sizeof(double))); CK(cudaMalloc(&dip.p, n * sizeof(int))); CK(cudaMalloc(&dib.p, n * sizeof(int)));
+    CK(cudaMalloc(&dxn.p, (size_t)n * P.dim * sizeof(double))); CK(cudaMalloc(&dxo.p, (size_t)n * P.dim * sizeof(double)));
+    CK(cudaMalloc(&dS.p, n * sizeof(double)));
+    CK(cudaMemcpyAsync(dR.p, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(dip.p, ip, n * sizeof(int), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(dib.p, ib, n * sizeof(int), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(dxn.p, xnew, (size_t)n * P.dim * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(dxo.p, xold, (size_t)n * P.dim * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CK(launch_update_action(P.trap, P, n, (const double*)dR.p, (const int*)dip.p, (const int*)dib.p, (const double*)dxn.p,
+                            (const double*)dxo.p, (double*)dS.p, h->st));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(DeltaS, dS.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return PIGS_OK;
+}
+
+static int unit_call(pigs_ctx* h, int op, int n, const std::vector<double>& in, size_t out_per, const double* out_init, double* out) {
+    DevBuf din, dout;
+    CK(cudaMalloc(&din.p, in.size() * sizeof(double)));
+    CK(cudaMalloc(&dout.p, (size_t)n * out_per * sizeof(double)));
+    CK(cudaMemcpyAsync(din.p, in.data(), in.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    if (out_init) CK(cudaMemcpyAsync(dout.p, out_init, (size_t)n * out_per * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    UnitArgs A; A.op = op; A.n = n; A.in = (const double*)din.p; A.out = (double*)dout.p;
+    CK(launch_unit(h->P.trap, h->P, A, h->st));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(out, dout.p, (size_t)n * out_per * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return PIGS_OK;
+}
+extern "C" int pigs_local_energy(pigs_handle h, int n, const double* R, double* E, double* Kin, double* Pot) {
+    NEED(h);
+    if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
+    if (n < 0 || !R) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;
+    std::vector<double> soa, out((size_t)3 * n);
+    to_soa(h->P, n, R, soa);
+    int rc = unit_call(h, U_LOCAL_ENERGY, n, soa, 3, nullptr, out.data());
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) { if (E) E[i] = out[3 * i]; if (Kin) Kin[i] = out[3 * i + 1]; if (Pot) Pot[i] = out[3 * i + 2]; }
+    return PIGS_OK;
+}
+extern "C" int pigs_therm_energy(pigs_handle h, int n, const double* Path, double* E, double* Ec, double* Ep) {
+    NEED(h);
+    if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
+    if (n < 0 || !Path) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;
+    std::vector<double> soa, out((size_t)3 * n);
+    to_soa(h->P, (long long)n * h->P.S, Path, soa);
+    int rc = unit_call(h, U_THERM_ENERGY, n, soa, 3, nullptr, out.data());
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) { if (E) E[i] = out[3 * i]; if (Ec) Ec[i] = out[3 * i + 1]; if (Ep) Ep[i] = out[3 * i + 2]; }
+    return PIGS_OK;
+}
+extern "C" int pigs_pair_correlation(pigs_handle h, int n, const double* R, double* gr) {
+    NEED(h);
+    if (h->P.trap) return fail(PIGS_E_ARG, "PairCorrelation is not defined in trap mode (vpi.f90:466)");
+    if (n < 0 || !R || !gr) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;
+    std::vector<double> soa;
+    to_soa(h->P, n, R, soa);
+    return unit_call(h, U_PAIR_CORR, n, soa, h->P.Nbin, gr, gr);
+}
+extern "C" int pigs_structure_factor(pigs_handle h, int n, const double* R, double* Sk) {
+    NEED(h);
+    if (h->P.trap) return fail(PIGS_E_ARG, "StructureFactor is not defined in trap mode (vpi.f90:466)");
+    if (n < 0 || !R || !Sk) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;
+    std::vector<double> soa;
+    to_soa(h->P, n, R, soa);
+    return unit_call(h, U_SOFK, n, soa, (size_t)h->P.Nk * h->P.dim, Sk, Sk);
+}
+extern "C" int pigs_obdm(pigs_handle h, int n, const double* xend, double* nrho) {
+    NEED(h);
+    if (h->P.trap) return fail(PIGS_E_ARG, "OBDM is not defined in trap mode (vpi.f90:400)");
+    if (n < 0 || !xend || !nrho) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;
+    const int dim = h->P.dim;
+    std::vector<double> xe((size_t)n * 6, 0.0);
+    for (int c = 0; c < n; ++c) for (int j = 0; j < 2; ++j) for (int k = 0; k < dim; ++k) xe[(size_t)c * 6 + j * 3 + k] = xend[((size_t)c * 2 + j) * dim + k];
+    return unit_call(h, U_OBDM, n, xe, (size_t)h->P.Nbin * (h->P.Npw + 1), nrho, nrho);
+}
+
+extern "C" int pigs_measure_fp64_peak(int device, double* tflops) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(PIGS_E_CUDA, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(PIGS_E_ARG, "bad device ordinal");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double* sink = nullptr;
+    CK(cudaMalloc((void**)&sink, sizeof(double)));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(a, 0));
+        CK(launch_dfma_peak(blocks, threads, iters, sink, 0));
+        CK(cudaEventRecord(b, 0));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        double fl = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    if (tflops) *tflops = best;
+    return PIGS_OK;
+}

@@ -1,0 +1,174 @@
+// pigs_unit.cu -- unit-API kernels (one reference procedure per launch, on
+// caller data), layout transposes, the chain reduction of block accumulators
+// and the FP64 peak micro-benchmark.  They reuse the device functions of the
+// persistent sweep kernel, so a unit-parity test exercises the production code.
+#include "pigs_launch.h"
+
+namespace pigs {
+
+// dispatcher over the 8 separately compiled sweep instantiations
+#define DECL(mt, var) cudaError_t sweep_l_##mt##_##var(int, const DevParams*, const SweepArgs*, int, int, size_t, cudaStream_t, int*);
+DECL(0, 0) DECL(0, 1) DECL(0, 2) DECL(0, 3) DECL(1, 0) DECL(1, 1) DECL(1, 2) DECL(1, 3)
+#undef DECL
+typedef cudaError_t (*sweep_fn)(int, const DevParams*, const SweepArgs*, int, int, size_t, cudaStream_t, int*);
+static sweep_fn pick(int mt, int var) {
+    static const sweep_fn tab[2][4] = {{sweep_l_0_0, sweep_l_0_1, sweep_l_0_2, sweep_l_0_3},
+                                       {sweep_l_1_0, sweep_l_1_1, sweep_l_1_2, sweep_l_1_3}};
+    return tab[mt ? 1 : 0][var & 3];
+}
+cudaError_t launch_sweep(int mt, int var, const DevParams& P, const SweepArgs& A, int grid, int block, size_t smem, cudaStream_t st) {
+    return pick(mt, var)(0, &P, &A, grid, block, smem, st, nullptr);
+}
+cudaError_t sweep_set_smem(int mt, int var, size_t smem) { return pick(mt, var)(1, nullptr, nullptr, 0, 0, smem, 0, nullptr); }
+cudaError_t sweep_occupancy(int mt, int var, int block, size_t smem, int* n) { return pick(mt, var)(2, nullptr, nullptr, 0, block, smem, 0, n); }
+
+// ---------------------------------------------------------------- estimators on caller data
+template <int VAR>
+__global__ void __launch_bounds__(128) k_unit(const __grid_constant__ DevParams P, const __grid_constant__ UnitArgs A) {
+    extern __shared__ __align__(16) double smem[];
+    Chain<false, VAR> C(P);
+    C.T.V = P.vtab; C.T.W = P.logwf;
+    C.G.tid = threadIdx.x; C.G.size = blockDim.x; C.G.warp = threadIdx.x >> 5; C.G.lane = threadIdx.x & 31;
+    C.G.nwarps = blockDim.x >> 5; C.G.bar = 1;
+    C.sm.part = smem;
+    C.sm.seg_old = C.sm.seg_new = C.sm.bc = C.sm.pp = nullptr; C.sm.ibc = nullptr;
+    const size_t ss = (size_t)3 * P.NpS;
+    for (int n = blockIdx.x; n < A.n; n += gridDim.x) {
+        if (A.op == U_LOCAL_ENERGY) {
+            double E, K, V;
+            C.LocalEnergy(A.in + n * ss, E, K, V);
+            if (threadIdx.x == 0) { A.out[3 * n] = E; A.out[3 * n + 1] = K; A.out[3 * n + 2] = V; }
+        } else if (A.op == U_THERM_ENERGY) {
+            double E, Ec, Ep;
+            C.path = const_cast<double*>(A.in) + n * ss * P.S;
+            C.ThermEnergy(E, Ec, Ep);
+            if (threadIdx.x == 0) { A.out[3 * n] = E; A.out[3 * n + 1] = Ec; A.out[3 * n + 2] = Ep; }
+        } else if (A.op == U_PAIR_CORR) {
+            C.PairCorrelation(A.in + n * ss, A.out + (size_t)n * P.Nbin);
+        } else if (A.op == U_SOFK) {
+            C.StructureFactor(A.in + n * ss, A.out + (size_t)n * P.Nk * P.dim);
+        } else if (A.op == U_OBDM) {
+            C.xend = const_cast<double*>(A.in) + (size_t)n * 6;
+            C.OBDM(A.out + (size_t)n * P.Nbin * (P.Npw + 1));
+        }
+        C.G.sync();
+    }
+}
+cudaError_t launch_unit(bool trap, const DevParams& P, const UnitArgs& A, cudaStream_t st) {
+    int grid = A.n < 1184 ? A.n : 1184;
+    size_t sm = 4 * 8 * sizeof(double);
+    if (trap) k_unit<3><<<grid, 128, sm, st>>>(P, A);
+    else k_unit<0><<<grid, 128, sm, st>>>(P, A);
+    return cudaGetLastError();
+}
+
+// UpdateAction (vpi_mod.f90:2491-2530): one warp per evaluation
+template <bool TRAP>
+__global__ void __launch_bounds__(128) k_update_action(const __grid_constant__ DevParams P, int n, const double* Rsoa,
+                                                      const int* ip, const int* ib, const double* xnew,
+                                                      const double* xold, double* dS) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    Tabs T; T.V = P.vtab; T.W = P.logwf;
+    for (int e = w; e < n; e += nw) {
+        double xo[3] = {0, 0, 0}, xn[3] = {0, 0, 0}, a[8];
+        for (int k = 0; k < P.dim; ++k) { xo[k] = xold[e * P.dim + k]; xn[k] = xnew[e * P.dim + k]; }
+        bead_partial<TRAP, false, false>(P, T, Rsoa + (size_t)e * 3 * P.NpS, ip[e] - 1, ib[e], lane, 32, lane == 0, xo, xn, a);
+        double v = warp_sum8(a, lane);
+        double t = dS_term(P, ib[e], lane >> 2, v);
+        t += shx(t, 4); t += shx(t, 8); t += shx(t, 16);
+        if (lane == 0) dS[e] = t;
+    }
+}
+cudaError_t launch_update_action(bool trap, const DevParams& P, int n, const double* Rsoa, const int* ip, const int* ib,
+                                 const double* xnew, const double* xold, double* dS, cudaStream_t st) {
+    int blocks = (n + 3) / 4;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    if (trap) k_update_action<true><<<blocks, 128, 0, st>>>(P, n, Rsoa, ip, ib, xnew, xold, dS);
+    else k_update_action<false><<<blocks, 128, 0, st>>>(P, n, Rsoa, ip, ib, xnew, xold, dS);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- layout transposes
+// aos: [chain][ib][ip][dim]  <->  soa: [chain][ib][3][NpS]
+__global__ void k_aos_to_soa(const __grid_constant__ DevParams P, const double* aos, double* soa, long long nslice) {
+    const long long per = (long long)3 * P.NpS;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nslice * per; i += (long long)gridDim.x * blockDim.x) {
+        long long s = i / per;
+        int r = (int)(i - s * per), k = r / P.NpS, ip = r - k * P.NpS;
+        double v = 0.0;
+        if (k < P.dim && ip < P.Np) v = aos[(s * P.Np + ip) * P.dim + k];
+        soa[i] = v;
+    }
+}
+__global__ void k_soa_to_aos(const __grid_constant__ DevParams P, const double* soa, double* aos, long long nslice) {
+    const long long per = (long long)P.Np * P.dim;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nslice * per; i += (long long)gridDim.x * blockDim.x) {
+        long long s = i / per;
+        int r = (int)(i - s * per), ip = r / P.dim, k = r - ip * P.dim;
+        aos[i] = soa[(s * 3 + k) * P.NpS + ip];
+    }
+}
+cudaError_t launch_aos_to_soa(const DevParams& P, const double* aos, double* soa, int nchain, cudaStream_t st) {
+    long long nslice = (long long)nchain * P.S;
+    k_aos_to_soa<<<148 * 8, 256, 0, st>>>(P, aos, soa, nslice);
+    return cudaGetLastError();
+}
+cudaError_t launch_soa_to_aos(const DevParams& P, const double* soa, double* aos, int nchain, cudaStream_t st) {
+    long long nslice = (long long)nchain * P.S;
+    k_soa_to_aos<<<148 * 8, 256, 0, st>>>(P, soa, aos, nslice);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- block accumulators
+// vec[i] = sum over chains, fixed order (deterministic).  One warp per element:
+// lanes stride the chains, then a shuffle tree.
+__global__ void k_reduce_block(const __grid_constant__ DevParams P, double* vec) {
+    const int nvec = NE + NCNT + (P.nacc - NE);
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int i = w; i < nvec; i += nw) {
+        double s = 0.0;
+        for (int c = lane; c < P.n_chains; c += 32) {
+            if (i < NE) s += P.acc[(size_t)c * P.nacc + i];
+            else if (i < NE + NCNT) s += (double)P.cnt[(size_t)c * NCNT + (i - NE)];
+            else s += P.acc[(size_t)c * P.nacc + (i - NCNT)];
+        }
+        s = warp_sum(s);
+        if (lane == 0) vec[i] = s;
+    }
+}
+cudaError_t launch_reduce_block(const DevParams& P, double* vec, cudaStream_t st) {
+    k_reduce_block<<<148, 256, 0, st>>>(P, vec);
+    return cudaGetLastError();
+}
+__global__ void k_zero_block(const __grid_constant__ DevParams P) {
+    const long long n = (long long)P.n_chains * P.nacc;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) P.acc[i] = 0.0;
+}
+cudaError_t launch_zero_block(const DevParams& P, cudaStream_t st) {
+    k_zero_block<<<148 * 2, 256, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- FP64 peak
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+cudaError_t launch_dfma_peak(int blocks, int threads, int iters, double* sink, cudaStream_t st) {
+    k_dfma_peak<<<blocks, threads, 0, st>>>(iters, sink);
+    return cudaGetLastError();
+}
+
+}  // namespace pigs

