@@ -6,12 +6,16 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 using namespace pigs;
 
 static thread_local std::string g_err;
+// one parameter block per translation unit lives in __constant__ memory: the
+// (upload, launch) pairs of different handles must not interleave
+static std::mutex g_launch_mutex;
 static int fail(int code, const std::string& m) { g_err = m; return code; }
 #define CK(call)                                                                                           \
     do {                                                                                                   \
@@ -50,10 +54,12 @@ static SweepArgs base_args(pigs_ctx* h) {
     A.chain_only = -1;
     A.groups_per_cta = h->G;
     A.threads_per_chain = h->T;
-    A.var = h->var;
+    A.tshift = 0;
+    while ((1 << A.tshift) < h->T) ++A.tshift;
     return A;
 }
 static int launch(pigs_ctx* h, const SweepArgs& A) {
+    std::lock_guard<std::mutex> lk(g_launch_mutex);
     CK(launch_sweep(h->mt, h->var, h->P, A, h->grid, h->block, h->smem, h->st));
     h->launches += 1;
     return PIGS_OK;
@@ -74,7 +80,7 @@ static int plan(pigs_ctx* h) {
         while (T * 2 <= want && T < 256) T *= 2;
     }
     if (T != 32 && T != 64 && T != 128 && T != 256 && T != 512) return fail(PIGS_E_ARG, "threads_per_chain must be 0,32,64,128,256,512");
-    const size_t gbytes = grp_smem_doubles(h->P.S, h->P.Np, T / 32) * sizeof(double);
+    const size_t gbytes = (grp_smem_bytes(h->P.S, h->P.Np, T / 32) + 15) & ~(size_t)15;
     const size_t tabbytes = (size_t)(p.Nmax + 2) * sizeof(double);
     int Gmax = 1024 / T;
     if (T > 32 && Gmax > 16) Gmax = 16;        // named barriers 0..15
@@ -519,8 +525,9 @@ extern "C" int pigs_update_action(pigs_handle h, int n, const double* R, const i
     CK(cudaMemcpyAsync(dib.p, ib, n * sizeof(int), cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(dxn.p, xnew, (size_t)n * P.dim * sizeof(double), cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(dxo.p, xold, (size_t)n * P.dim * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    { std::lock_guard<std::mutex> lk(g_launch_mutex);
     CK(launch_update_action(P.trap, P, n, (const double*)dR.p, (const int*)dip.p, (const int*)dib.p, (const double*)dxn.p,
-                            (const double*)dxo.p, (double*)dS.p, h->st));
+                            (const double*)dxo.p, (double*)dS.p, h->st)); }
     h->launches += 1;
     CK(cudaMemcpyAsync(DeltaS, dS.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -534,7 +541,8 @@ static int unit_call(pigs_ctx* h, int op, int n, const std::vector<double>& in, 
     CK(cudaMemcpyAsync(din.p, in.data(), in.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
     if (out_init) CK(cudaMemcpyAsync(dout.p, out_init, (size_t)n * out_per * sizeof(double), cudaMemcpyHostToDevice, h->st));
     UnitArgs A; A.op = op; A.n = n; A.in = (const double*)din.p; A.out = (double*)dout.p;
-    CK(launch_unit(h->P.trap, h->P, A, h->st));
+    { std::lock_guard<std::mutex> lk(g_launch_mutex);
+    CK(launch_unit(h->P.trap, h->P, A, h->st)); }
     h->launches += 1;
     CK(cudaMemcpyAsync(out, dout.p, (size_t)n * out_per * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));

@@ -8,8 +8,15 @@
 // computed redundantly or broadcast through shared memory, so all branching on
 // Monte-Carlo state is group-uniform.  The pair sums of one bead-update
 // (reference: UpdateAction, vpi_mod.f90:2491-2530) are spread over the lanes of
-// a warp, partner j <-> lane, and reduced with a halving butterfly of warp
-// shuffles; beads of one move are spread over the warps of the group.
+// a warp, partner j <-> lane, and reduced with warp shuffles; beads of one move
+// are spread over the warps of the group.
+//
+// Code-size discipline (ncu, round 1: the first version inlined everything and
+// stalled 10 of 22 warp-cycles per issue on instruction fetch, and kept its
+// context object in local memory): run parameters live in __constant__ memory
+// (they fold into FP64 instruction operands), per-group state lives in shared
+// memory, and every shared helper is a real (noinline) function so the 14 moves
+// are thin glue around one copy of the hot code.
 //
 // Data layout in HBM (per chain): path[ib][k][ip] -- structure-of-arrays per
 // time slice so that lane<->partner loads are unit-stride and coalesced
@@ -56,91 +63,131 @@ struct DevParams {
     int off_gr, off_sk, off_nr;
 };
 
+// what the persistent kernel is asked to do
+enum SweepOp { OP_BLOCK = 0, OP_MOVE = 1, OP_UNIFORM = 2, OP_GAUSS = 3, OP_SEED = 4 };
+struct SweepArgs {
+    int op;
+    int nstep;           // OP_BLOCK: steps; OP_UNIFORM/OP_GAUSS: draws
+    int move, ip0, half; // OP_MOVE
+    int chain_only;      // >=0: only that chain (OP_UNIFORM/OP_GAUSS/OP_SEED)
+    int seed;            // OP_SEED
+    int groups_per_cta, threads_per_chain, tshift;   // T = 1 << tshift
+    int* accepted;       // OP_MOVE [n_chains]
+    int* aux;            // OP_MOVE [n_chains]
+    double* draws;       // OP_UNIFORM/OP_GAUSS [n]
+};
+
+// one copy per translation unit; the TU's launcher uploads them (stream-ordered)
+// right before its kernel launch
+static __constant__ DevParams cP;
+static __constant__ SweepArgs cA;
+
 // ------------------------------------------------------------------ group
 struct Grp {
-    int tid, size, warp, lane, nwarps, bar;
-    __device__ __forceinline__ void sync() const {
-        if (size == 32) __syncwarp();
-        else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(size) : "memory");
-    }
+    int tid, lane, warp, nwarps, size;
 };
-
-// per-group shared-memory scratch (carved from dynamic smem)
-struct GrpSmem {
-    double* seg_old;   // [3][S]   beads of the moved particle before the move
-    double* seg_new;   // [3][S]   ... proposed
-    double* part;      // [max(nwarps,4)*8] partial sums / reduction scratch
-    double* bc;        // [8] broadcast slots
-    double* pp;        // [Np] swap probabilities
-    int*    ibc;       // [8] int broadcast
-};
-// layout: seg_old[3S] seg_new[3S] part[np*8] bc[8] pp[Np] ibc[8 ints] eacc[NE] cnt[NCNT]
-__host__ __device__ inline size_t grp_smem_doubles(int S, int Np, int nwarps) {
-    int np = nwarps < 4 ? 4 : nwarps;
-    return (size_t)6 * S + (size_t)np * 8 + 8 + (size_t)Np + 4 /*8 ints*/ + NE + NCNT;
+__device__ __forceinline__ Grp grp() {
+    Grp g;
+    g.size = cA.threads_per_chain;
+    g.tid = threadIdx.x & (g.size - 1);
+    g.lane = threadIdx.x & 31;
+    g.warp = g.tid >> 5;
+    g.nwarps = g.size >> 5;
+    return g;
+}
+__device__ __forceinline__ void gsync() {
+    if (cA.threads_per_chain == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x >> cA.tshift)), "r"(cA.threads_per_chain) : "memory");
 }
 
-// ------------------------------------------------------------------ tables
-// TABMODE 0: both tables through the read-only L1/L2 path; 1: VTable in shared
-// memory, LogWF global; 2: both in shared memory.
-struct Tabs {
-    const double* V;
-    const double* W;
+// per-group state in shared memory: header + arrays
+struct GS {
+    double* path;        // this chain
+    double* xend;        // this chain, [2][3]
+    double* acc;         // this chain's accumulators (global)
+    int* cyc;
+    int* hist;
+    unsigned* mt;
+    const double* tabV;  // table bases: shared-memory copies when staged, else global
+    const double* tabW;
+    double bc[8];        // broadcast slots
+    double eacc[NE];
+    long long cnt[NCNT];
+    int ibc[8];
+    // chain state (written by thread 0, read by all after a group sync)
+    int mti, isopen, iworm0, iperm, new_pc, end_pc, ik0, swap_acc, idiag_aux, chain, pad0, pad1;
+    // followed by: seg_old[3S] seg_new[3S] part[np*8] pp[Np]
 };
+__host__ __device__ inline int part_slots(int nwarps) { return nwarps < 4 ? 4 : nwarps; }
+__host__ __device__ inline size_t grp_smem_bytes(int S, int Np, int nwarps) {
+    return sizeof(GS) + sizeof(double) * ((size_t)6 * S + (size_t)part_slots(nwarps) * 8 + (size_t)Np);
+}
+__device__ __forceinline__ double* seg_old(GS* gs) { return reinterpret_cast<double*>(gs + 1); }
+__device__ __forceinline__ double* seg_new(GS* gs) { return seg_old(gs) + 3 * cP.S; }
+__device__ __forceinline__ double* part_of(GS* gs) { return seg_old(gs) + 6 * cP.S; }
+__device__ __forceinline__ double* pp_of(GS* gs) { return part_of(gs) + part_slots(cA.threads_per_chain >> 5) * 8; }
+__device__ __forceinline__ double& so(GS* gs, int k, int ib) { return seg_old(gs)[k * cP.S + ib]; }
+__device__ __forceinline__ double& sn(GS* gs, int k, int ib) { return seg_new(gs)[k * cP.S + ib]; }
+__device__ __forceinline__ double* slice(GS* gs, int ib) { return gs->path + (size_t)ib * 3 * cP.NpS; }
+__device__ __forceinline__ double& pth(GS* gs, int k, int ip0, int ib) { return gs->path[((size_t)ib * 3 + k) * cP.NpS + ip0]; }
+
+// ------------------------------------------------------------------ tables
+// VAR 0: both tables through the read-only L1/L2 path; 1: VTable in shared
+// memory, LogWF global; 2: both in shared memory; 3: trap (tables global).
+template <int VAR> struct VarTraits;
+template <> struct VarTraits<0> { static constexpr bool TRAP = false, VSM = false, WSM = false; };
+template <> struct VarTraits<1> { static constexpr bool TRAP = false, VSM = true,  WSM = false; };
+template <> struct VarTraits<2> { static constexpr bool TRAP = false, VSM = true,  WSM = true;  };
+template <> struct VarTraits<3> { static constexpr bool TRAP = true,  VSM = false, WSM = false; };
+
 template <bool SM>
 __device__ __forceinline__ double tld(const double* t, int i) {
     if (SM) return t[i];
     return __ldg(t + i);
 }
 
-// Interpolate(opt,...) of interpolate.f90:1-45 with x/dx -> x*inv_dx (every
-// interpolant is continuous in x, so an index flip at a grid point is harmless).
+// Interpolate(opt,...) of interpolate.f90:1-45, fast form for the hot loop:
+// x/dx -> x*inv_dx and floor() by the 2^52 trick (no F2I/I2F conversions).
+// Every interpolant is continuous in x, so an index flip at a grid point is
+// harmless.
 struct Lk {
-    int i0;
-    double a1, a2;
+    int i0;          // = ix-1
+    double a1, a2;   // aux1, aux2 of interpolate.f90:14-15
 };
-__device__ __forceinline__ Lk lk_prep(double r, double dr, double inv_dr, int Nmax) {
+__device__ __forceinline__ Lk lk_prep(double r) {
+    const double MAGIC = 6755399441055744.0;                 // 2^52 + 2^51
+    double m = fma(r, cP.inv_dr, -0.5) + MAGIC;              // round-to-nearest of (t - 1/2) == floor(t) off grid points
     Lk k;
-    double t = r * inv_dr;
-    int i0 = (int)t;                    // = ix-1
-    i0 = max(1, min(i0, Nmax - 1));     // keep i0-1 .. i0+2 inside (0:Nmax+1); never active for r in (dr, rcut)
-    k.i0 = i0;
-    k.a1 = fma(-(double)i0, dr, r);     // aux1 = x-(ix-1)*dx
-    k.a2 = dr - k.a1;
+    k.i0 = max(__double2loint(m), 1);                        // r >= dr always in practice; keeps i0-1 in range
+    double tf = m - MAGIC;
+    k.a1 = fma(-tf, cP.dr, r);
+    k.a2 = cP.dr - k.a1;
     return k;
 }
 template <bool SM>
-__device__ __forceinline__ double lk_val(const double* F, const Lk& k, double inv_dr) {   // opt 0
-    return (k.a1 * tld<SM>(F, k.i0 + 1) + k.a2 * tld<SM>(F, k.i0)) * inv_dr;
+__device__ __forceinline__ double lk_val(const double* F, const Lk& k) {   // opt 0
+    return (k.a1 * tld<SM>(F, k.i0 + 1) + k.a2 * tld<SM>(F, k.i0)) * cP.inv_dr;
 }
 template <bool SM>
-__device__ __forceinline__ void lk_val_d1(const double* F, const Lk& k, double inv_dr, double& v, double& d1) {   // opt 0 and 1
+__device__ __forceinline__ void lk_val_d1(const double* F, const Lk& k, double& v, double& d1) {   // opt 0 and 1
     double fm = tld<SM>(F, k.i0 - 1), f0 = tld<SM>(F, k.i0), f1 = tld<SM>(F, k.i0 + 1), f2 = tld<SM>(F, k.i0 + 2);
     double Fc = k.a1 * f1 + k.a2 * f0;
     double Fb = k.a1 * f0 + k.a2 * fm;
     double Fa = k.a1 * f2 + k.a2 * f1;
-    v = Fc * inv_dr;
-    d1 = 0.5 * (Fa - Fb) * inv_dr * inv_dr;
-}
-template <bool SM>
-__device__ __forceinline__ void lk_d1_d2(const double* F, const Lk& k, double inv_dr, double& d1, double& d2) {   // opt 1 and 2
-    double fm = tld<SM>(F, k.i0 - 1), f0 = tld<SM>(F, k.i0), f1 = tld<SM>(F, k.i0 + 1), f2 = tld<SM>(F, k.i0 + 2);
-    double Fc = k.a1 * f1 + k.a2 * f0;
-    double Fb = k.a1 * f0 + k.a2 * fm;
-    double Fa = k.a1 * f2 + k.a2 * f1;
-    d1 = 0.5 * (Fa - Fb) * inv_dr * inv_dr;
-    d2 = (Fa - 2.0 * Fc + Fb) * inv_dr * inv_dr * inv_dr;
+    v = Fc * cP.inv_dr;
+    d1 = (Fa - Fb) * (0.5 * cP.inv_dr * cP.inv_dr);
 }
 
-// Interpolate opt 1 and 2 in the reference's exact operation order, true
+// Interpolate opt 0, 1 and 2 in the reference's exact operation order, true
 // divisions, no FMA contraction.  The second difference divides rounding noise
 // by dx^2 (~1e7): only the same arithmetic reproduces the reference's value to
 // 1e-10, so the mixed estimator (2 calls per MC step, not the hot loop) pays
 // for IEEE divisions here.
 template <bool SM>
-__device__ __forceinline__ void lk_exact_d1_d2(const double* F, double x, double dx, int Nmax, double& d1, double& d2) {
+__device__ __forceinline__ void lk_exact_d1_d2(const double* F, double x, double& d1, double& d2) {
+    const double dx = cP.dr;
     int ix = (int)__ddiv_rn(x, dx) + 1;
-    ix = max(2, min(ix, Nmax));
+    ix = max(2, min(ix, cP.Nmax));
     double aux1 = __dadd_rn(x, -__dmul_rn((double)(ix - 1), dx));
     double aux2 = __dadd_rn(dx, -aux1);
     double fm = tld<SM>(F, ix - 2), f0 = tld<SM>(F, ix - 1), f1 = tld<SM>(F, ix), f2 = tld<SM>(F, ix + 1);
@@ -151,9 +198,10 @@ __device__ __forceinline__ void lk_exact_d1_d2(const double* F, double x, double
     d2 = __ddiv_rn(__dadd_rn(__dadd_rn(Fa, -__dmul_rn(2.0, Fc)), Fb), __dmul_rn(dx, dx));
 }
 template <bool SM>
-__device__ __forceinline__ double lk_exact_val(const double* F, double x, double dx, int Nmax) {
+__device__ __forceinline__ double lk_exact_val(const double* F, double x) {
+    const double dx = cP.dr;
     int ix = (int)__ddiv_rn(x, dx) + 1;
-    ix = max(2, min(ix, Nmax));
+    ix = max(2, min(ix, cP.Nmax));
     double aux1 = __dadd_rn(x, -__dmul_rn((double)(ix - 1), dx));
     double aux2 = __dadd_rn(dx, -aux1);
     return __ddiv_rn(__dadd_rn(__dmul_rn(aux1, tld<SM>(F, ix)), __dmul_rn(aux2, tld<SM>(F, ix - 1))), dx);
@@ -206,6 +254,13 @@ __device__ __forceinline__ double warp_sum8(const double (&a)[8], int lane) {
     d += shx(d, 1);
     return d;      // value index = lane>>2
 }
+// two values: lanes 0..15 end with the sum of a, lanes 16..31 with the sum of b
+__device__ __forceinline__ double warp_sum2(double a, double b, int lane) {
+    const bool h16 = lane & 16;
+    double v = (h16 ? b : a) + shx(h16 ? a : b, 16);
+    v += shx(v, 8); v += shx(v, 4); v += shx(v, 2); v += shx(v, 1);
+    return v;
+}
 
 // ------------------------------------------------------------------ RNG
 // MT19937 with the 1998 seeding, bit-faithful to random_mod.f90:5-115.  State
@@ -215,7 +270,8 @@ __device__ inline void mt_seed(unsigned* mt, int& mti, unsigned seed) {
     for (int i = 1; i < 624; ++i) mt[i] = 69069u * mt[i - 1];
     mti = 624;
 }
-__device__ inline unsigned mt_next(unsigned* mt, int& mti) {
+static __device__ __noinline__ unsigned mt_next(unsigned* mt, int* pmti) {
+    int mti = *pmti;
     if (mti >= 624) {
         if (mti == 625) mt_seed(mt, mti, 4357u);
         for (int kk = 0; kk < 624; ++kk) {
@@ -225,54 +281,41 @@ __device__ inline unsigned mt_next(unsigned* mt, int& mti) {
         mti = 0;
     }
     unsigned y = mt[mti++];
+    *pmti = mti;
     y ^= (y >> 11);
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
     y ^= (y >> 18);
     return y;
 }
-__device__ inline double mt_grnd(unsigned* mt, int& mti) {        // [0,1] inclusive
-    return (double)mt_next(mt, mti) / 4294967295.0;
+__device__ __forceinline__ double mt_grnd(GS* gs) {                 // [0,1] inclusive
+    return (double)mt_next(gs->mt, &gs->mti) / 4294967295.0;
 }
-__device__ inline double mt_rangauss(unsigned* mt, int& mti) {    // random_mod.f90:195-219, first deviate
+static __device__ __noinline__ double mt_rangauss(GS* gs) {                // random_mod.f90:195-219, first deviate
     double u1, u2, w;
     do {
-        u1 = 2.0 * mt_grnd(mt, mti) - 1.0;
-        u2 = 2.0 * mt_grnd(mt, mti) - 1.0;
+        u1 = 2.0 * mt_grnd(gs) - 1.0;
+        u2 = 2.0 * mt_grnd(gs) - 1.0;
         w = u1 * u1 + u2 * u2;
     } while (!(w <= 1.0));
     w = sqrt((-2.0 * log(w)) / w);
     return u1 * w;
 }
 
-// Philox4x32-10 (Salmon et al., SC'11)
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+// Philox4x32-10 (Salmon et al., SC'11); counter = (ctr_lo, ctr_hi, chain, tag), key = seed
+static __device__ __noinline__ uint4 philox_at(unsigned long long c, unsigned chain) {
+    uint4 x = make_uint4((unsigned)c, (unsigned)(c >> 32), chain, 0x50494753u);
+    unsigned k0 = (unsigned)cP.seed, k1 = (unsigned)(cP.seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
+        unsigned hi0 = __umulhi(0xD2511F53u, x.x), lo0 = 0xD2511F53u * x.x;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, x.z), lo1 = 0xCD9E8D57u * x.z;
+        x = make_uint4(hi1 ^ x.y ^ k0, lo1, hi0 ^ x.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
     }
-    return c;
+    return x;
 }
-
-template <bool MT>
-struct Rng {
-    // MT replay
-    unsigned* mt;
-    int mti;
-    // Philox
-    unsigned long long ctr;
-    uint2 key;
-    unsigned chain;
-    int slot;      // broadcast slot toggle (group-uniform)
-
-    __device__ __forceinline__ uint4 philox_at(unsigned long long c) const {
-        return philox4x32_10(make_uint4((unsigned)c, (unsigned)(c >> 32), chain, 0x50494753u), key);
-    }
-};
 __device__ __forceinline__ double u01_from(unsigned lo, unsigned hi) {        // [0,1)
     unsigned long long x = ((unsigned long long)hi << 32) | lo;
     return (double)(x >> 11) * (1.0 / 9007199254740992.0);
@@ -280,15 +323,15 @@ __device__ __forceinline__ double u01_from(unsigned lo, unsigned hi) {        //
 
 // one uniform, identical in every thread of the group
 template <bool MT>
-__device__ __forceinline__ double rng_uniform(const Grp& G, Rng<MT>& rng, const GrpSmem& sm) {
+__device__ __forceinline__ double rng_uniform(GS* gs, unsigned long long& ctr) {
     if (MT) {
-        rng.slot ^= 1;
-        if (G.tid == 0) sm.bc[rng.slot] = mt_grnd(rng.mt, rng.mti);
-        G.sync();
-        return sm.bc[rng.slot];
+        gsync();
+        if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) gs->bc[0] = mt_grnd(gs);
+        gsync();
+        return gs->bc[0];
     } else {
-        uint4 r = rng.philox_at(rng.ctr);
-        rng.ctr += 1;
+        uint4 r = philox_at(ctr, (unsigned)gs->chain);
+        ctr += 1;
         return u01_from(r.x, r.y);
     }
 }
@@ -296,125 +339,146 @@ __device__ __forceinline__ double rng_uniform(const Grp& G, Rng<MT>& rng, const 
 // seg_new[k*S + bead] in the reference's draw order (bead-major, component-minor).
 // Ends with a group sync.
 template <bool MT>
-__device__ __forceinline__ void rng_gauss_fill(const Grp& G, Rng<MT>& rng, const GrpSmem& sm, int S, int dim,
-                                               int b0, int bstride, int nb) {
+static __device__ __noinline__ void rng_gauss_fill(GS* gs, unsigned long long* pctr, int dim, int b0, int bstride, int nb) {
+    const Grp G = grp();
     const int n = nb * dim;
+    double* dst = seg_new(gs);
     if (MT) {
         if (G.tid == 0) {
             for (int i = 0; i < n; ++i) {
                 int j = i / dim, k = i - j * dim;
-                sm.seg_new[k * S + b0 + j * bstride] = mt_rangauss(rng.mt, rng.mti);
+                dst[k * cP.S + b0 + j * bstride] = mt_rangauss(gs);
             }
         }
     } else {
+        unsigned long long ctr = *pctr;
         for (int i = G.tid; i < n; i += G.size) {
             int j = i / dim, k = i - j * dim;
-            uint4 r = rng.philox_at(rng.ctr + (unsigned long long)i);
+            uint4 r = philox_at(ctr + (unsigned long long)i, (unsigned)gs->chain);
             double u1 = 1.0 - u01_from(r.x, r.y);       // (0,1]
             double u2 = u01_from(r.z, r.w);
-            sm.seg_new[k * S + b0 + j * bstride] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+            dst[k * cP.S + b0 + j * bstride] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
         }
-        rng.ctr += (unsigned long long)n;
+        *pctr = ctr + (unsigned long long)n;
     }
-    G.sync();
+    gsync();
 }
 
 // ------------------------------------------------------------------ the pair sums of one bead-update
-// Values accumulated per lane for one displaced bead (UpdatePot, vpi_mod.f90:2660-2841,
+// Per-lane partial sums for one displaced bead (UpdatePot, vpi_mod.f90:2660-2841,
 // UpdateWf, :2534-2656), old and new position against partner j:
 //   a[0] = PotNew-PotOld   a[1] = PsiNew-PsiOld
 //   a[2..4] = Fnew(k)      a[5..7] = Fold(k)
 // KIND: 0 interior even slice, 1 odd slice (Chin force term), 2 end slice (Jastrow).
-template <int KIND, bool TRAP, bool VSM, bool WSM>
-__device__ __forceinline__ void pair_one(const DevParams& P, const Tabs& T, double x0, double x1, double x2,
-                                         double rx, double ry, double rz, bool is_new, double sgn, double (&a)[8]) {
+//
+// Branch-free: a partner outside the cutoff (or the moved particle itself) is
+// evaluated at r = rcut with weight 0, so the new and old positions of two
+// partners form four independent dependency chains the scheduler can overlap.
+template <int KIND, bool TRAP, bool VSM, bool WSM, bool IS_NEW>
+__device__ __forceinline__ void pair_one(const double* tV, const double* tW, bool valid, double x0, double x1, double x2,
+                                         double rx, double ry, double rz, double (&a)[8]) {
     double d0 = x0 - rx, d1 = x1 - ry, d2 = x2 - rz;
     if (!TRAP) {
-        d0 = mimg(d0, P.L[0], P.Lh[0]);
-        d1 = mimg(d1, P.L[1], P.Lh[1]);
-        d2 = mimg(d2, P.L[2], P.Lh[2]);
+        d0 = mimg(d0, cP.L[0], cP.Lh[0]);
+        d1 = mimg(d1, cP.L[1], cP.Lh[1]);
+        d2 = mimg(d2, cP.L[2], cP.Lh[2]);
     }
     double r2 = d0 * d0 + d1 * d1 + d2 * d2;
     // PBC: both positions cut at rcut (Q24).  Trap: UpdatePot cuts only the OLD
     // position (Q12), UpdateWf cuts nothing.
-    bool in_pot = TRAP ? (is_new || r2 <= P.rcut2) : (r2 <= P.rcut2);
-    bool in_wf = TRAP ? true : in_pot;
-    if (in_pot || (KIND == 2 && in_wf)) {
-        double r = sqrt(r2);
-        Lk k = lk_prep(r, P.dr, P.inv_dr, P.Nmax);
-        if (in_pot) {
-            if (KIND == 1) {
-                double v, dv;
-                lk_val_d1<VSM>(T.V, k, P.inv_dr, v, dv);
-                a[0] += sgn * v;
-                double s = dv / r;
-                int o = is_new ? 2 : 5;
-                a[o] += s * d0; a[o + 1] += s * d1; a[o + 2] += s * d2;
-            } else {
-                a[0] += sgn * lk_val<VSM>(T.V, k, P.inv_dr);
-            }
-        }
-        if (KIND == 2) a[1] += sgn * lk_val<WSM>(T.W, k, P.inv_dr);
+    const bool in_pot = valid && (TRAP ? (IS_NEW || r2 <= cP.rcut2) : (r2 <= cP.rcut2));
+    const bool in_wf = TRAP ? valid : in_pot;
+    const bool any = (KIND == 2) ? in_wf : in_pot;
+    double r2c = any ? r2 : cP.rcut2;
+    double ir = rsqrt(r2c);
+    double r = r2c * ir;
+    Lk k = lk_prep(r);
+    if (TRAP) k.i0 = min(k.i0, cP.Nmax - 1);
+    const double sgn = IS_NEW ? 1.0 : -1.0;
+    if (KIND == 1) {
+        double v, dv;
+        lk_val_d1<VSM>(tV, k, v, dv);
+        a[0] += in_pot ? sgn * v : 0.0;
+        double s = in_pot ? dv * ir : 0.0;
+        constexpr int o = IS_NEW ? 2 : 5;
+        a[o] += s * d0; a[o + 1] += s * d1; a[o + 2] += s * d2;
+    } else {
+        double v = lk_val<VSM>(tV, k);
+        a[0] += in_pot ? sgn * v : 0.0;
+    }
+    if (KIND == 2) {
+        double w = lk_val<WSM>(tW, k);
+        a[1] += in_wf ? sgn * w : 0.0;
     }
 }
 
 template <int KIND, bool TRAP, bool VSM, bool WSM>
-__device__ __forceinline__ void pair_loop(const DevParams& P, const Tabs& T, const double* Rx, int ip0, int j0, int jstride,
-                                          const double (&xo)[3], const double (&xn)[3], double (&a)[8]) {
-    const double* Ry = Rx + P.NpS;
-    const double* Rz = Ry + P.NpS;
-    for (int j = j0; j < P.Np; j += jstride) {
-        if (j == ip0) continue;
+__device__ __forceinline__ void pair_loop(const double* tV, const double* tW, const double* Rx, int ip0, int j0,
+                                          int jstride, const double (&xo)[3], const double (&xn)[3], double (&a)[8]) {
+    const double* Ry = Rx + cP.NpS;
+    const double* Rz = Ry + cP.NpS;
+    for (int j = j0; j < cP.Np; j += jstride) {
+        const bool valid = (j != ip0);
         double rx = Rx[j], ry = Ry[j], rz = Rz[j];
-        pair_one<KIND, TRAP, VSM, WSM>(P, T, xn[0], xn[1], xn[2], rx, ry, rz, true, 1.0, a);
-        pair_one<KIND, TRAP, VSM, WSM>(P, T, xo[0], xo[1], xo[2], rx, ry, rz, false, -1.0, a);
+        pair_one<KIND, TRAP, VSM, WSM, true>(tV, tW, valid, xn[0], xn[1], xn[2], rx, ry, rz, a);
+        pair_one<KIND, TRAP, VSM, WSM, false>(tV, tW, valid, xo[0], xo[1], xo[2], rx, ry, rz, a);
     }
 }
 
-__device__ __forceinline__ int bead_kind(int ib, int Nb) { return (ib == 0 || ib == 2 * Nb) ? 2 : (ib & 1); }
+__device__ __forceinline__ int bead_kind(int ib) { return (ib == 0 || ib == 2 * cP.Nb) ? 2 : (ib & 1); }
 
 // lane-partial sums of one bead against partners j0, j0+jstride, ...; the lane
 // with add_self adds the one-body (trap) terms once.
 template <bool TRAP, bool VSM, bool WSM>
-__device__ __forceinline__ void bead_partial(const DevParams& P, const Tabs& T, const double* Rx, int ip0, int ib,
-                                             int j0, int jstride, bool add_self, const double (&xo)[3],
-                                             const double (&xn)[3], double (&a)[8]) {
+__device__ __forceinline__ void bead_partial(const double* tV, const double* tW, const double* Rx, int ip0, int ib, int j0,
+                                             int jstride, bool add_self, const double (&xo)[3], const double (&xn)[3],
+                                             double (&a)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = 0.0;
-    const int kind = bead_kind(ib, P.Nb);
+    const int kind = bead_kind(ib);
     if (TRAP && add_self) {
-        for (int k = 0; k < P.dim; ++k) {          // system_mod.f90:213-252
-            double ak = P.a_ho[k], a2 = ak * ak, a4 = a2 * a2;
-            a[0] += 0.5 * xn[k] * xn[k] / a4 - 0.5 * xo[k] * xo[k] / a4;
-            if (kind == 1) { a[2 + k] += xn[k] / a4; a[5 + k] += xo[k] / a4; }
-            if (kind == 2) a[1] += -0.5 * (xn[k] / ak) * (xn[k] / ak) + 0.5 * (xo[k] / ak) * (xo[k] / ak);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {          // system_mod.f90:213-252
+            if (k < cP.dim) {
+                double ak = cP.a_ho[k], a2 = ak * ak, a4 = a2 * a2;
+                a[0] += 0.5 * xn[k] * xn[k] / a4 - 0.5 * xo[k] * xo[k] / a4;
+                if (kind == 1) { a[2 + k] += xn[k] / a4; a[5 + k] += xo[k] / a4; }
+                if (kind == 2) a[1] += -0.5 * (xn[k] / ak) * (xn[k] / ak) + 0.5 * (xo[k] / ak) * (xo[k] / ak);
+            }
         }
     }
-    if (kind == 0) pair_loop<0, TRAP, VSM, WSM>(P, T, Rx, ip0, j0, jstride, xo, xn, a);
-    else if (kind == 1) pair_loop<1, TRAP, VSM, WSM>(P, T, Rx, ip0, j0, jstride, xo, xn, a);
-    else pair_loop<2, TRAP, VSM, WSM>(P, T, Rx, ip0, j0, jstride, xo, xn, a);
+    if (kind == 0) pair_loop<0, TRAP, VSM, WSM>(tV, tW, Rx, ip0, j0, jstride, xo, xn, a);
+    else if (kind == 1) pair_loop<1, TRAP, VSM, WSM>(tV, tW, Rx, ip0, j0, jstride, xo, xn, a);
+    else pair_loop<2, TRAP, VSM, WSM>(tV, tW, Rx, ip0, j0, jstride, xo, xn, a);
 }
 
 // DeltaS of UpdateAction from the eight reduced values
 // (GreenFunction opt 0, global_mod.f90:29-46).
-__device__ __forceinline__ double assemble_dS(const DevParams& P, int ib, const double (&v)[8]) {
-    const int kind = bead_kind(ib, P.Nb);
-    double dt = P.dt;
+__device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
+    const int kind = bead_kind(ib);
+    double dt = cP.dt;
     if (kind == 2) return -v[1] + dt * v[0] / 3.0;
     if (kind == 0) return 2.0 * dt * v[0] / 3.0;
     double f2 = (v[2] * v[2] + v[3] * v[3] + v[4] * v[4]) - (v[5] * v[5] + v[6] * v[6] + v[7] * v[7]);
     return 4.0 * dt * (v[0] + dt * dt * f2 / 6.0) / 3.0;
 }
-// the same, distributed: lane holds value index q = lane>>2 (after warp_sum8);
-// returns the lane's additive term of DeltaS.
-__device__ __forceinline__ double dS_term(const DevParams& P, int ib, int q, double val) {
-    const int kind = bead_kind(ib, P.Nb);
-    double dt = P.dt;
-    if (q == 0) return (kind == 2 ? dt / 3.0 : (kind == 0 ? 2.0 * dt / 3.0 : 4.0 * dt / 3.0)) * val;
-    if (q == 1) return kind == 2 ? -val : 0.0;
-    if (kind != 1) return 0.0;
-    double c = 4.0 * dt * dt * dt / 18.0;
-    return (q < 5 ? c : -c) * val * val;
+// Whole-warp DeltaS of one bead from the per-lane partial sums, identical in
+// every lane; the reduction is specialised by bead class (1, 2 or 7 values).
+__device__ __forceinline__ double warp_dS(int ib, const double (&a)[8], int lane) {
+    const int kind = bead_kind(ib);
+    const double dt = cP.dt;
+    if (kind == 0) return (2.0 * dt / 3.0) * warp_sum(a[0]);
+    if (kind == 2) {
+        double v = warp_sum2(a[0], a[1], lane);
+        double t = (lane & 16) ? -v : (dt / 3.0) * v;
+        return t + shx(t, 16);
+    }
+    double v = warp_sum8(a, lane);
+    const int q = lane >> 2;
+    const double c = 4.0 * dt * dt * dt / 18.0;
+    double t = (q == 0) ? (4.0 * dt / 3.0) * v : ((q == 1) ? 0.0 : ((q < 5) ? c * v * v : -c * v * v));
+    t += shx(t, 4); t += shx(t, 8); t += shx(t, 16);
+    return t;
 }
 
 }  // namespace pigs

@@ -1,8 +1,9 @@
 // pigs_launch.h -- host-visible launchers of the kernels (one translation unit
-// per sweep-kernel instantiation so they compile in parallel).
+// per sweep-kernel instantiation so they compile in parallel).  Every launcher
+// uploads its translation unit's __constant__ parameter block on the same
+// stream right before the launch; the C API serialises launches with a mutex.
 #pragma once
 #include "pigs_device.cuh"
-#include "pigs_sweep.cuh"
 
 namespace pigs {
 

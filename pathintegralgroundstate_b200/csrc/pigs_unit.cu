@@ -3,6 +3,8 @@
 // and the FP64 peak micro-benchmark.  They reuse the device functions of the
 // persistent sweep kernel, so a unit-parity test exercises the production code.
 #include "pigs_launch.h"
+#include "pigs_sweep.cuh"
+#include <cstring>
 
 namespace pigs {
 
@@ -23,70 +25,86 @@ cudaError_t sweep_set_smem(int mt, int var, size_t smem) { return pick(mt, var)(
 cudaError_t sweep_occupancy(int mt, int var, int block, size_t smem, int* n) { return pick(mt, var)(2, nullptr, nullptr, 0, block, smem, 0, n); }
 
 // ---------------------------------------------------------------- estimators on caller data
+// one CTA (= one chain group of 128 threads) per configuration
 template <int VAR>
-__global__ void __launch_bounds__(128) k_unit(const __grid_constant__ DevParams P, const __grid_constant__ UnitArgs A) {
+__global__ void __launch_bounds__(128) k_unit(const __grid_constant__ UnitArgs A) {
     extern __shared__ __align__(16) double smem[];
-    Chain<false, VAR> C(P);
-    C.T.V = P.vtab; C.T.W = P.logwf;
-    C.G.tid = threadIdx.x; C.G.size = blockDim.x; C.G.warp = threadIdx.x >> 5; C.G.lane = threadIdx.x & 31;
-    C.G.nwarps = blockDim.x >> 5; C.G.bar = 1;
-    C.sm.part = smem;
-    C.sm.seg_old = C.sm.seg_new = C.sm.bc = C.sm.pp = nullptr; C.sm.ibc = nullptr;
-    const size_t ss = (size_t)3 * P.NpS;
+    GS* gs = reinterpret_cast<GS*>(smem);
+    if (threadIdx.x == 0) { gs->tabV = cP.vtab; gs->tabW = cP.logwf; gs->chain = 0; }
+    __syncthreads();
+    const size_t ss = (size_t)3 * cP.NpS;
     for (int n = blockIdx.x; n < A.n; n += gridDim.x) {
         if (A.op == U_LOCAL_ENERGY) {
-            double E, K, V;
-            C.LocalEnergy(A.in + n * ss, E, K, V);
-            if (threadIdx.x == 0) { A.out[3 * n] = E; A.out[3 * n + 1] = K; A.out[3 * n + 2] = V; }
+            double e[3];
+            LocalEnergy<VAR>(gs, A.in + n * ss, e);
+            if (threadIdx.x == 0) { A.out[3 * n] = e[0]; A.out[3 * n + 1] = e[1]; A.out[3 * n + 2] = e[2]; }
         } else if (A.op == U_THERM_ENERGY) {
-            double E, Ec, Ep;
-            C.path = const_cast<double*>(A.in) + n * ss * P.S;
-            C.ThermEnergy(E, Ec, Ep);
-            if (threadIdx.x == 0) { A.out[3 * n] = E; A.out[3 * n + 1] = Ec; A.out[3 * n + 2] = Ep; }
+            double e[3];
+            if (threadIdx.x == 0) gs->path = const_cast<double*>(A.in) + n * ss * cP.S;
+            __syncthreads();
+            ThermEnergy<VAR>(gs, e);
+            if (threadIdx.x == 0) { A.out[3 * n] = e[0]; A.out[3 * n + 1] = e[1]; A.out[3 * n + 2] = e[2]; }
         } else if (A.op == U_PAIR_CORR) {
-            C.PairCorrelation(A.in + n * ss, A.out + (size_t)n * P.Nbin);
+            PairCorrelation(A.in + n * ss, A.out + (size_t)n * cP.Nbin);
         } else if (A.op == U_SOFK) {
-            C.StructureFactor(A.in + n * ss, A.out + (size_t)n * P.Nk * P.dim);
+            StructureFactor(A.in + n * ss, A.out + (size_t)n * cP.Nk * cP.dim);
         } else if (A.op == U_OBDM) {
-            C.xend = const_cast<double*>(A.in) + (size_t)n * 6;
-            C.OBDM(A.out + (size_t)n * P.Nbin * (P.Npw + 1));
+            OBDM(A.in + (size_t)n * 6, A.out + (size_t)n * cP.Nbin * (cP.Npw + 1));
         }
-        C.G.sync();
+        __syncthreads();
     }
 }
+static cudaError_t upload(const DevParams& P, int T, cudaStream_t st) {
+    SweepArgs A;
+    memset(&A, 0, sizeof A);
+    A.chain_only = -1; A.groups_per_cta = 1; A.threads_per_chain = T;
+    A.tshift = 0; while ((1 << A.tshift) < T) ++A.tshift;
+    cudaError_t e = cudaMemcpyToSymbolAsync(cP, &P, sizeof(DevParams), 0, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbolAsync(cA, &A, sizeof(SweepArgs), 0, cudaMemcpyHostToDevice, st);
+}
 cudaError_t launch_unit(bool trap, const DevParams& P, const UnitArgs& A, cudaStream_t st) {
+    cudaError_t e = upload(P, 128, st);
+    if (e != cudaSuccess) return e;
     int grid = A.n < 1184 ? A.n : 1184;
-    size_t sm = 4 * 8 * sizeof(double);
-    if (trap) k_unit<3><<<grid, 128, sm, st>>>(P, A);
-    else k_unit<0><<<grid, 128, sm, st>>>(P, A);
+    size_t sm = grp_smem_bytes(P.S, P.Np, 4);
+    if (trap) {
+        e = cudaFuncSetAttribute(k_unit<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        k_unit<3><<<grid, 128, sm, st>>>(A);
+    } else {
+        e = cudaFuncSetAttribute(k_unit<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        k_unit<0><<<grid, 128, sm, st>>>(A);
+    }
     return cudaGetLastError();
 }
 
 // UpdateAction (vpi_mod.f90:2491-2530): one warp per evaluation
 template <bool TRAP>
-__global__ void __launch_bounds__(128) k_update_action(const __grid_constant__ DevParams P, int n, const double* Rsoa,
-                                                      const int* ip, const int* ib, const double* xnew,
-                                                      const double* xold, double* dS) {
+__global__ void __launch_bounds__(128) k_update_action(int n, const double* Rsoa, const int* ip, const int* ib,
+                                                      const double* xnew, const double* xold, double* dS) {
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    Tabs T; T.V = P.vtab; T.W = P.logwf;
     for (int e = w; e < n; e += nw) {
         double xo[3] = {0, 0, 0}, xn[3] = {0, 0, 0}, a[8];
-        for (int k = 0; k < P.dim; ++k) { xo[k] = xold[e * P.dim + k]; xn[k] = xnew[e * P.dim + k]; }
-        bead_partial<TRAP, false, false>(P, T, Rsoa + (size_t)e * 3 * P.NpS, ip[e] - 1, ib[e], lane, 32, lane == 0, xo, xn, a);
-        double v = warp_sum8(a, lane);
-        double t = dS_term(P, ib[e], lane >> 2, v);
-        t += shx(t, 4); t += shx(t, 8); t += shx(t, 16);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) if (k < cP.dim) { xo[k] = xold[e * cP.dim + k]; xn[k] = xnew[e * cP.dim + k]; }
+        bead_partial<TRAP, false, false>(cP.vtab, cP.logwf, Rsoa + (size_t)e * 3 * cP.NpS, ip[e] - 1, ib[e], lane, 32,
+                                         lane == 0, xo, xn, a);
+        double t = warp_dS(ib[e], a, lane);
         if (lane == 0) dS[e] = t;
     }
 }
 cudaError_t launch_update_action(bool trap, const DevParams& P, int n, const double* Rsoa, const int* ip, const int* ib,
                                  const double* xnew, const double* xold, double* dS, cudaStream_t st) {
+    cudaError_t e = upload(P, 128, st);
+    if (e != cudaSuccess) return e;
     int blocks = (n + 3) / 4;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    if (trap) k_update_action<true><<<blocks, 128, 0, st>>>(P, n, Rsoa, ip, ib, xnew, xold, dS);
-    else k_update_action<false><<<blocks, 128, 0, st>>>(P, n, Rsoa, ip, ib, xnew, xold, dS);
+    if (trap) k_update_action<true><<<blocks, 128, 0, st>>>(n, Rsoa, ip, ib, xnew, xold, dS);
+    else k_update_action<false><<<blocks, 128, 0, st>>>(n, Rsoa, ip, ib, xnew, xold, dS);
     return cudaGetLastError();
 }
 
