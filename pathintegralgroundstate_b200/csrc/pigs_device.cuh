@@ -339,7 +339,7 @@ __device__ __forceinline__ double rng_uniform(GS* gs, unsigned long long& ctr) {
 // seg_new[k*S + bead] in the reference's draw order (bead-major, component-minor).
 // Ends with a group sync.
 template <bool MT>
-static __device__ __noinline__ void rng_gauss_fill(GS* gs, unsigned long long* pctr, int dim, int b0, int bstride, int nb) {
+__device__ __forceinline__ void rng_gauss_fill(GS* gs, unsigned long long* pctr, int dim, int b0, int bstride, int nb) {
     const Grp G = grp();
     const int n = nb * dim;
     double* dst = seg_new(gs);
@@ -353,7 +353,7 @@ static __device__ __noinline__ void rng_gauss_fill(GS* gs, unsigned long long* p
     } else {
         unsigned long long ctr = *pctr;
         for (int i = G.tid; i < n; i += G.size) {
-            int j = i / dim, k = i - j * dim;
+            int j = dim == 3 ? (i * 43691) >> 17 : (dim == 2 ? i >> 1 : i), k = i - j * dim;
             uint4 r = philox_at(ctr + (unsigned long long)i, (unsigned)gs->chain);
             double u1 = 1.0 - u01_from(r.x, r.y);       // (0,1]
             double u2 = u01_from(r.z, r.w);
@@ -417,6 +417,7 @@ __device__ __forceinline__ void pair_loop(const double* tV, const double* tW, co
                                           int jstride, const double (&xo)[3], const double (&xn)[3], double (&a)[8]) {
     const double* Ry = Rx + cP.NpS;
     const double* Rz = Ry + cP.NpS;
+#pragma unroll 1
     for (int j = j0; j < cP.Np; j += jstride) {
         const bool valid = (j != ip0);
         double rx = Rx[j], ry = Ry[j], rz = Rz[j];

@@ -44,374 +44,356 @@ __device__ __forceinline__ void bump(GS* gs, int c) {
     if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) gs->cnt[c] += 1;
 }
 
-// ---------------------------------------------------------------- segment I/O
-static __device__ __noinline__ void load_segment(GS* gs, int ip0, int ii, int ie) {
-    const Grp G = grp();
-    const int n = ie - ii + 1;
-    for (int i = G.tid; i < 3 * n; i += G.size) {
-        int k = i / n, ib = ii + (i - k * n);
-        double v = pth(gs, k, ip0, ib);
-        so(gs, k, ib) = v;
-        sn(gs, k, ib) = v;
-    }
-    gsync();
-}
-static __device__ __noinline__ void commit(GS* gs, int ip0, int ii, int ie) {
-    const Grp G = grp();
-    const int n = ie - ii + 1;
-    if (n > 0) {
-        for (int i = G.tid; i < cP.dim * n; i += G.size) {
-            int k = i / n, ib = ii + (i - k * n);
-            pth(gs, k, ip0, ib) = sn(gs, k, ib);
-        }
-    }
-    gsync();
-}
-
-// ---------------------------------------------------------------- proposals
-// free end: xnew = BC(unwrap(anchor) + sigma*g)    (vpi_mod.f90:619-645 / 758-785)
-template <int VAR>
-static __device__ __noinline__ void free_end_transform(GS* gs, int iend, int ianchor, double sigma, bool next) {
-    const Grp G = grp();
-    if (G.tid < cP.dim) {
-        int k = G.tid;
-        double xold = so(gs, k, iend), g = sn(gs, k, iend), anc = sn(gs, k, ianchor), base;
-        if (next) base = xold - wrap_lt<VAR>(k, xold - anc);
-        else base = xold + wrap_lt<VAR>(k, anc - xold);
-        sn(gs, k, iend) = bc_wrap<VAR>(k, base + sigma * g);
-    }
-    gsync();
-}
-// Levy bridge between ii and ie over the interior beads (vpi_mod.f90:509-549)
-template <int VAR>
-static __device__ __noinline__ void stage_transform(GS* gs, int ii, int L, int ie) {
-    const Grp G = grp();
-    if (G.tid < cP.dim) {
-        int k = G.tid;
-        double pnext = sn(gs, k, ie);
-        for (int j = 1; j <= L - 1; ++j) {
-            int ib = ii + j;
-            double xold = so(gs, k, ib), g = sn(gs, k, ib), pprev = sn(gs, k, ib - 1);
-            double xprev = xold + wrap_lt<VAR>(k, pprev - xold);
-            double xnext = xold - wrap_lt<VAR>(k, xold - pnext);
-            double sigma = sqrt((double)((float)(L - j) / (float)(L - j + 1)) * cP.dt);   // float32 ratio (Q15)
-            double xmid = (xnext + xprev * (double)(L - j)) / (double)(L - j + 1);
-            sn(gs, k, ib) = bc_wrap<VAR>(k, xmid + sigma * g);
-        }
-    }
-    gsync();
-}
-// one bisection level (vpi_mod.f90:905-956)
-template <int VAR>
-static __device__ __noinline__ void bisect_transform(GS* gs, int ii, int delta_ib, int nb) {
-    const Grp G = grp();
-    double sigma = sqrt(0.5 * (0.5 * (double)delta_ib * cP.dt));
-    for (int i = G.tid; i < nb * cP.dim; i += G.size) {
-        int j = i / cP.dim, k = i - j * cP.dim;
-        int iprev = ii + j * delta_ib, inext = iprev + delta_ib, icurr = (iprev + inext) / 2;
-        double xold = so(gs, k, icurr), g = sn(gs, k, icurr);
-        double xprev = xold + wrap_lt<VAR>(k, sn(gs, k, iprev) - xold);
-        double xnext = xold - wrap_lt<VAR>(k, xold - sn(gs, k, inext));
-        sn(gs, k, icurr) = bc_wrap<VAR>(k, 0.5 * (xprev + xnext) + sigma * g);
-    }
-    gsync();
+// ---------------------------------------------------------------- small-integer helpers (no IDIV in hot code)
+__device__ __forceinline__ int div_dim(int i) {          // i / cP.dim for dim in 1..3, 0 <= i < 65536
+    return cP.dim == 3 ? (i * 43691) >> 17 : (cP.dim == 2 ? i >> 1 : i);
 }
 
 // ---------------------------------------------------------------- action
 // Sum over beads ib = b0 + m*bstride (m<nb) of w_m * DeltaS(ip,ib,seg_new,seg_old),
 // w_0 = wfirst, w_{nb-1} = wlast, else 1.  Identical in every thread.
+// Work split: with at least as many beads as warps each warp takes whole beads
+// (split = 1) and reduces to DeltaS with shuffles only; with fewer beads the
+// partners of a bead are divided over `split` warps and combined through smem.
 template <int VAR>
-static __device__ __noinline__ double eval_action(GS* gs, int ip0, int b0, int bstride, int nb, double wfirst, double wlast) {
-    const Grp G = grp();
+__device__ __forceinline__ double eval_action(GS* gs, const Grp& G, int ip0, int b0, int bstride, int nb, double wfirst,
+                                              double wlast) {
     if (G.tid == 0) {
         for (int m = 0; m < nb; ++m) gs->cnt[C_UPD_EVEN + bead_kind(b0 + m * bstride)] += 1;
     }
-    const int nw = G.nwarps, nch = (cP.Np + 31) >> 5;
+    const int nw = G.nwarps;
     int split = 1;
-    if (nb < nw) { split = nw / nb; if (split > nch) split = nch; }
+    if (nb < nw) {
+        const int nch = (cP.Np + 31) >> 5;
+        split = nw / nb;
+        if (split > nch) split = nch;
+    }
     const double* tV = gs->tabV;
     const double* tW = gs->tabW;
-    double xo[3], xn[3], a[8];
-    if (split == 1) {
-        double Sw = 0.0;
-        for (int m = G.warp; m < nb; m += nw) {
-            int ib = b0 + m * bstride;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { xo[k] = so(gs, k, ib); xn[k] = sn(gs, k, ib); }
-            bead_partial<PIGS_TRAP, PIGS_VSM, PIGS_WSM>(tV, tW, slice(gs, ib), ip0, ib, G.lane, 32, G.lane == 0, xo, xn, a);
-            double t = warp_dS(ib, a, G.lane);
-            double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
-            Sw += w * t;
-        }
-        if (nw == 1) return Sw;
-        double* part = part_of(gs);
-        if (G.lane == 0) part[G.warp] = Sw;
-        gsync();
-        double S = 0.0;
-        for (int w = 0; w < nw; ++w) S += part[w];
-        gsync();
-        return S;
-    }
     double* part = part_of(gs);
     const int ntask = nb * split;
-    if (G.warp < ntask) {
-        int m = G.warp / split, s = G.warp - m * split;
-        int ib = b0 + m * bstride;
+    double Sw = 0.0;
+    for (int task = G.warp; task < ntask; task += nw) {
+        int m = task, s = 0;
+        if (split > 1) { m = task / split; s = task - m * split; }
+        const int ib = b0 + m * bstride;
+        double xo[3], xn[3], a[8];
 #pragma unroll
         for (int k = 0; k < 3; ++k) { xo[k] = so(gs, k, ib); xn[k] = sn(gs, k, ib); }
         bead_partial<PIGS_TRAP, PIGS_VSM, PIGS_WSM>(tV, tW, slice(gs, ib), ip0, ib, s * 32 + G.lane, 32 * split,
                                                    (s == 0) && (G.lane == 0), xo, xn, a);
-        double v = warp_sum8(a, G.lane);
-        if ((G.lane & 3) == 0) part[G.warp * 8 + (G.lane >> 2)] = v;
-    }
-    gsync();
-    double S = 0.0;
-    for (int m = 0; m < nb; ++m) {
-        double v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            double acc = 0.0;
-            for (int s = 0; s < split; ++s) acc += part[(m * split + s) * 8 + q];
-            v[q] = acc;
+        if (split == 1) {
+            double t = warp_dS(ib, a, G.lane);
+            double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
+            Sw += w * t;
+        } else {
+            double v = warp_sum8(a, G.lane);
+            if ((G.lane & 3) == 0) part[task * 8 + (G.lane >> 2)] = v;
         }
-        double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
-        S += w * assemble_dS(b0 + m * bstride, v);
+    }
+    if (nw == 1) return Sw;
+    double S = 0.0;
+    if (split == 1) {
+        if (G.lane == 0) part[G.warp] = Sw;
+        gsync();
+        for (int w = 0; w < nw; ++w) S += part[w];
+    } else {
+        gsync();
+        for (int m = 0; m < nb; ++m) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                double acc = 0.0;
+                for (int s = 0; s < split; ++s) acc += part[(m * split + s) * 8 + q];
+                v[q] = acc;
+            }
+            double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
+            S += w * assemble_dS(b0 + m * bstride, v);
+        }
     }
     gsync();
     return S;
-}
-// the Metropolis question (e.g. vpi_mod.f90:356-364): a uniform is consumed only if exp(-S)<1
-PIGS_T __device__ __noinline__ bool metropolis(GS* gs, ull* pctr, double S) {
-    if (S <= 0.0) return true;                 // exp(-S) >= 1 without evaluating it
-    double e = exp(-S);
-    if (e >= 1.0) return true;                 // (tiny positive S; NaN falls through and is rejected after its draw, Q23)
-    ull ctr = *pctr;
-    double u = rng_uniform<MT>(gs, ctr);
-    *pctr = ctr;
-    return e >= u;
 }
 PIGS_T __device__ __forceinline__ double uniform(GS* gs, ull& ctr) { return rng_uniform<MT>(gs, ctr); }
 PIGS_T __device__ __forceinline__ int draw_int(GS* gs, ull& ctr, int n) {       // int(n*grnd()), clamped for u==1 (Q6)
     int v = (int)((double)n * rng_uniform<MT>(gs, ctr));
     return v >= n ? (n > 0 ? n - 1 : 0) : v;
 }
-PIGS_T __device__ __forceinline__ void gauss_fill(GS* gs, ull& ctr, int b0, int bstride, int nb) {
-    rng_gauss_fill<MT>(gs, &ctr, cP.dim, b0, bstride, nb);
-}
-
-// multilevel part shared by the three bisection moves (vpi_mod.f90:903-971).
-// Replay draws the Gaussians level by level (the reference's order); Philox
-// draws all 2^Nl-1 interior beads in one pass before the first level.
-PIGS_T __device__ __noinline__ bool bisect_levels(GS* gs, ull* pctr, int ip0, int ii, int Nl, bool prefilled) {
-    ull ctr = *pctr;
-    bool ok = true;
-    if (!MT && !prefilled) gauss_fill<MT, VAR>(gs, ctr, ii + 1, 1, (1 << Nl) - 1);
-    for (int ilev = 1; ilev <= Nl; ++ilev) {
-        int delta_ib = 1 << (Nl - ilev + 1), nb = 1 << (ilev - 1);
-        if (MT) gauss_fill<MT, VAR>(gs, ctr, ii + delta_ib / 2, delta_ib, nb);
-        bisect_transform<VAR>(gs, ii, delta_ib, nb);
-        double S = eval_action<VAR>(gs, ip0, ii + delta_ib / 2, delta_ib, nb, 1.0, 1.0);
-        if (!metropolis<MT, VAR>(gs, &ctr, S)) { ok = false; break; }
-    }
-    *pctr = ctr;
-    return ok;
-}
-
-// ---------------------------------------------------------------- the 14 moves
-PIGS_T __device__ __noinline__ void TranslateRange(GS* gs, ull* pctr, int ip0, int ibi, int ibf, int half) {
-    // TranslateChain (vpi_mod.f90:313-379) when half == 0, TranslateHalfChain (:383-476) otherwise
-    const Grp G = grp();
-    ull ctr = *pctr;
-    if (half) {
-        if (G.tid < cP.dim) pth(gs, G.tid, ip0, cP.Nb) = gs->xend[(half - 1) * 3 + G.tid];
-        gsync();
-    }
-    double dx[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) if (k < cP.dim) dx[k] = cP.delta_cm * (2.0 * uniform<MT, VAR>(gs, ctr) - 1.0);
-    const int n = ibf - ibi + 1;
-    for (int i = G.tid; i < 3 * n; i += G.size) {
-        int k = i / n, ib = ibi + (i - k * n);
-        double v = pth(gs, k, ip0, ib);
-        double d = (k == 0) ? dx[0] : ((k == 1) ? dx[1] : dx[2]);
-        so(gs, k, ib) = v;
-        sn(gs, k, ib) = (k < cP.dim) ? bc_wrap<VAR>(k, v + d) : v;
-    }
-    gsync();
-    double S = eval_action<VAR>(gs, ip0, ibi, 1, n, 1.0, 1.0);      // half-chain: cut bead at full weight (Q21)
-    if (metropolis<MT, VAR>(gs, &ctr, S)) {
-        bump(gs, half ? C_ACC_CM_HALF : C_ACC_CM);
-        if (half && G.tid < cP.dim) gs->xend[(half - 1) * 3 + G.tid] = sn(gs, G.tid, cP.Nb);
-        commit(gs, ip0, ibi, ibf);
-    }
-    *pctr = ctr;
-}
-// Staging (vpi_mod.f90:480-578) and StagingHalfChain (:1376-1491)
-PIGS_T __device__ __noinline__ void StagingMove(GS* gs, ull* pctr, int L, int ip0, int half) {
-    const Grp G = grp();
-    ull ctr = *pctr;
-    int ii;
-    if (half) {
-        if (G.tid < cP.dim) pth(gs, G.tid, ip0, cP.Nb) = gs->xend[(half - 1) * 3 + G.tid];
-        gsync();
-        ii = draw_int<MT, VAR>(gs, ctr, cP.Nb - L + 1) + (half == 1 ? 0 : cP.Nb);
-    } else {
-        ii = draw_int<MT, VAR>(gs, ctr, 2 * cP.Nb - L + 1);
-    }
-    int ie = ii + L;
-    load_segment(gs, ip0, ii, ie);
-    gauss_fill<MT, VAR>(gs, ctr, ii + 1, 1, L - 1);
-    stage_transform<VAR>(gs, ii, L, ie);
-    double S = eval_action<VAR>(gs, ip0, ii + 1, 1, L - 1, 1.0, 1.0);
-    // half-chain: interior beads never include the cut bead Nb, so xend(:,half) is unchanged on acceptance
-    if (metropolis<MT, VAR>(gs, &ctr, S)) { bump(gs, half ? C_ACC_BD_HALF : C_ACC_BD); commit(gs, ip0, ii + 1, ie - 1); }
-    *pctr = ctr;
-}
-// MoveHead (vpi_mod.f90:582-720) and MoveHeadHalfChain (:1495-1656)
-PIGS_T __device__ __noinline__ void HeadMove(GS* gs, ull* pctr, int Lmax, int ip0, int half) {
-    const Grp G = grp();
-    ull ctr = *pctr;
-    int Ls = draw_int<MT, VAR>(gs, ctr, Lmax - 1) + 2;
-    if (half) {
-        if (G.tid < cP.dim) pth(gs, G.tid, ip0, cP.Nb) = gs->xend[(half - 1) * 3 + G.tid];
-        gsync();
-    }
-    int ii = (half == 2) ? cP.Nb : 0, ie = ii + Ls;
-    load_segment(gs, ip0, ii, ie);
-    gauss_fill<MT, VAR>(gs, ctr, ii, 1, Ls);                   // free end, then beads ii+1..: the reference's order
-    free_end_transform<VAR>(gs, ii, ie, sqrt((double)Ls * cP.dt), true);
-    stage_transform<VAR>(gs, ii, Ls, ie);
-    double S = eval_action<VAR>(gs, ip0, ii, 1, Ls, (half == 2) ? 0.5 : 1.0, 1.0);   // cut bead weighs 1/2 (:1573-1577)
-    if (metropolis<MT, VAR>(gs, &ctr, S)) {
-        bump(gs, half ? C_ACC_HEAD_HALF : C_ACC_HEAD);
-        if (half == 2 && G.tid < cP.dim) gs->xend[3 + G.tid] = sn(gs, G.tid, cP.Nb);      // the free end IS the cut bead
-        commit(gs, ip0, ii, ie - 1);
-    }
-    *pctr = ctr;
-}
-// MoveTail (vpi_mod.f90:724-860) and MoveTailHalfChain (:1660-1817)
-PIGS_T __device__ __noinline__ void TailMove(GS* gs, ull* pctr, int Lmax, int ip0, int half) {
-    const Grp G = grp();
-    ull ctr = *pctr;
-    int Ls = draw_int<MT, VAR>(gs, ctr, Lmax - 1) + 2;
-    if (half) {
-        if (G.tid < cP.dim) pth(gs, G.tid, ip0, cP.Nb) = gs->xend[(half - 1) * 3 + G.tid];
-        gsync();
-    }
-    int ie = (half == 1) ? cP.Nb : 2 * cP.Nb, ii = ie - Ls;
-    load_segment(gs, ip0, ii, ie);
-    if (MT) { gauss_fill<MT, VAR>(gs, ctr, ie, 1, 1); gauss_fill<MT, VAR>(gs, ctr, ii + 1, 1, Ls - 1); }
-    else gauss_fill<MT, VAR>(gs, ctr, ii + 1, 1, Ls);
-    free_end_transform<VAR>(gs, ie, ii, sqrt((double)Ls * cP.dt), false);
-    stage_transform<VAR>(gs, ii, Ls, ie);
-    double S = eval_action<VAR>(gs, ip0, ii + 1, 1, Ls, 1.0, (half == 1) ? 0.5 : 1.0);   // (:1734-1738)
-    if (metropolis<MT, VAR>(gs, &ctr, S)) {
-        bump(gs, half ? C_ACC_TAIL_HALF : C_ACC_TAIL);
-        if (half == 1 && G.tid < cP.dim) gs->xend[G.tid] = sn(gs, G.tid, cP.Nb);
-        commit(gs, ip0, ii + 1, ie);
-    }
-    *pctr = ctr;
-}
-PIGS_T __device__ __noinline__ void Bisection(GS* gs, ull* pctr, int level, int ip0) {          // vpi_mod.f90:864-998
-    ull ctr = *pctr;
-    int Nl = level, ii = draw_int<MT, VAR>(gs, ctr, 2 * cP.Nb - (1 << Nl) + 1), ie = ii + (1 << Nl);
-    load_segment(gs, ip0, ii, ie);
-    if (bisect_levels<MT, VAR>(gs, &ctr, ip0, ii, Nl, false)) { bump(gs, C_ACC_BD); commit(gs, ip0, ii + 1, ie - 1); }
-    *pctr = ctr;
-}
-// MoveHeadBisection (vpi_mod.f90:1002-1184) when head, MoveTailBisection (:1188-1372) otherwise
-PIGS_T __device__ __noinline__ void EndBisection(GS* gs, ull* pctr, int level, int ip0, bool head) {
-    ull ctr = *pctr;
-    int Nl = draw_int<MT, VAR>(gs, ctr, level - 1) + 2;
-    int ii = head ? 0 : 2 * cP.Nb - (1 << Nl), ie = ii + (1 << Nl);
-    int iend = head ? ii : ie, ianc = head ? ie : ii;
-    load_segment(gs, ip0, ii, ie);
-    if (MT) gauss_fill<MT, VAR>(gs, ctr, iend, 1, 1);
-    else gauss_fill<MT, VAR>(gs, ctr, head ? ii : ii + 1, 1, 1 << Nl);      // free end and all interior beads in one pass
-    free_end_transform<VAR>(gs, iend, ianc, sqrt((double)(1 << Nl) * cP.dt), head);
-    double S0 = eval_action<VAR>(gs, ip0, iend, 1, 1, 1.0, 1.0);
-    if (metropolis<MT, VAR>(gs, &ctr, S0)) {
-        if (bisect_levels<MT, VAR>(gs, &ctr, ip0, ii, Nl, true)) {
-            bump(gs, head ? C_ACC_HEAD : C_ACC_TAIL);
-            if (head) commit(gs, ip0, ii, ie - 1); else commit(gs, ip0, ii + 1, ie);
-        }
-    }
-    *pctr = ctr;
-}
 // DeltaK of the broken/mended link (vpi_mod.f90:1859-1873, 2205-2219)
 template <int VAR>
 __device__ __forceinline__ double link_DeltaK(const double* seg, int ii, int ie, int Ls) {
     double r2 = 0.0;
-    for (int k = 0; k < cP.dim; ++k) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) if (k < cP.dim) {
         double d = seg[k * cP.S + ii] - seg[k * cP.S + ie];
         if (!PIGS_TRAP) d = mimg(d, cP.L[k], cP.Lh[k]);
         r2 += d * d;
     }
     return -0.5 * r2 / ((double)Ls * cP.dt) - 0.5 * (double)cP.dim * log(2.0 * cP.pi * (double)Ls * cP.dt);
 }
-PIGS_T __device__ __forceinline__ int draw_even_Ls(GS* gs, ull& ctr, int Lmax) { return 2 * draw_int<MT, VAR>(gs, ctr, (Lmax - 2) / 2) + 2; }
-PIGS_T __device__ __forceinline__ int draw_half(GS* gs, ull& ctr) { int h = (int)(uniform<MT, VAR>(gs, ctr) * 2.0) + 1; return h > 2 ? 2 : h; }
 
-// OpenChain (vpi_mod.f90:1821-2076) when open, CloseChain (:2080-2266) otherwise
-PIGS_T __device__ __noinline__ void OpenClose(GS* gs, ull* pctr, int Lmax, int ip0, bool open) {
+// ---------------------------------------------------------------- the move engine
+// Every move of vpi_mod.f90 is an instance of one pipeline; a descriptor word
+// selects the variant.  One copy of each stage => the hot code stays inside the
+// instruction cache and no stage is a function call.
+enum MoveFlags {
+    MV_TRANSLATE = 0, MV_BRIDGE = 1, MV_BISECT = 2, MV_TYPE_MASK = 3,
+    MV_HALF1 = 1 << 2, MV_HALF2 = 2 << 2, MV_HALF_MASK = 3 << 2,   // first Path(:,ip,Nb) = xend(:,half)
+    MV_FREE_NEXT = 1 << 4,        // free end = bead ii, anchored on ie    (head-like)
+    MV_FREE_PREV = 1 << 5,        // free end = bead ie, anchored on ii    (tail-like)
+    MV_WFIRST_HALF = 1 << 6,      // first evaluated bead weighs 1/2 (cut bead)
+    MV_WLAST_HALF = 1 << 7,       // last evaluated bead weighs 1/2
+    MV_GLUE_II_X1 = 1 << 8,       // seg_new(ii) = xend(:,1) before the bridge   (CloseChain, half 2)
+    MV_GLUE_IE_X2 = 1 << 9,       // seg_new(ie) = xend(:,2)                     (CloseChain half 1, Swap)
+    MV_DK_OLD_ADD = 1 << 10,      // + DeltaK of the old link                    (OpenChain)
+    MV_DK_NEW_SUB = 1 << 11,      // - DeltaK of the new link                    (CloseChain)
+};
+// [m0,m1] = beads evaluated and, on acceptance, committed.  Returns acceptance
+// (group-uniform).  seg_old/seg_new stay valid for the caller's epilogue.
+PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags, int ip0, int ii, int ie, int m0, int m1,
+                                                    double Sbase) {
     const Grp G = grp();
     ull ctr = *pctr;
-    int Ls = draw_even_Ls<MT, VAR>(gs, ctr, Lmax), half = draw_half<MT, VAR>(gs, ctr);
-    double Sum = open ? -cP.logCd : cP.logCd;
-    int ii = (half == 1) ? cP.Nb - Ls : cP.Nb, ie = ii + Ls;
-    load_segment(gs, ip0, ii, ie);
-    double DeltaK = 0.0;
-    if (open) {
-        DeltaK = link_DeltaK<VAR>(seg_old(gs), ii, ie, Ls);
-        if (half == 1) {
-            if (MT) { gauss_fill<MT, VAR>(gs, ctr, ie, 1, 1); gauss_fill<MT, VAR>(gs, ctr, ii + 1, 1, Ls - 1); }
-            else gauss_fill<MT, VAR>(gs, ctr, ii + 1, 1, Ls);
-            free_end_transform<VAR>(gs, ie, ii, sqrt((double)Ls * cP.dt), false);
-        } else {
-            gauss_fill<MT, VAR>(gs, ctr, ii, 1, Ls);
-            free_end_transform<VAR>(gs, ii, ie, sqrt((double)Ls * cP.dt), true);
-        }
-    } else {
-        if (G.tid < cP.dim) sn(gs, G.tid, cP.Nb) = gs->xend[(half == 1 ? 3 : 0) + G.tid];       // glue onto the other end
+    const int type = flags & MV_TYPE_MASK;
+    const int half = (flags & MV_HALF_MASK) >> 2;
+    const int L = ie - ii;
+    const int dim = cP.dim;
+    if (half) {
+        if (G.tid < dim) pth(gs, G.tid, ip0, cP.Nb) = gs->xend[(half - 1) * 3 + G.tid];
         gsync();
-        gauss_fill<MT, VAR>(gs, ctr, ii + 1, 1, Ls - 1);
     }
-    stage_transform<VAR>(gs, ii, Ls, ie);
-    double S;
-    if (half == 1) S = eval_action<VAR>(gs, ip0, ii + 1, 1, Ls, 1.0, 0.5);
-    else S = eval_action<VAR>(gs, ip0, ii, 1, Ls, 0.5, 1.0);
-    Sum += S;
-    if (!open) DeltaK = link_DeltaK<VAR>(seg_new(gs), ii, ie, Ls);
-    bool acc = metropolis<MT, VAR>(gs, &ctr, open ? Sum + DeltaK : Sum - DeltaK);
-    *pctr = ctr;
-    if (open) {
-        if (acc) {
-            bump(gs, C_ACC_OPEN);
-            if (G.tid < cP.dim) {
-                int k = G.tid;
-                gs->xend[k] = (half == 1) ? sn(gs, k, cP.Nb) : so(gs, k, cP.Nb);
-                gs->xend[3 + k] = (half == 1) ? so(gs, k, cP.Nb) : sn(gs, k, cP.Nb);
+    // ---- load the segment (translate: shifted copy)
+    {
+        double dx[3] = {0.0, 0.0, 0.0};
+        if (type == MV_TRANSLATE) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) if (k < dim) dx[k] = cP.delta_cm * (2.0 * uniform<MT, VAR>(gs, ctr) - 1.0);
+        }
+        const int n = L + 1;
+        for (int i = G.tid; i < 3 * n; i += G.size) {
+            int k = (i >= n) + (i >= 2 * n), ib = ii + (i - k * n);
+            double v = pth(gs, k, ip0, ib);
+            so(gs, k, ib) = v;
+            if (type == MV_TRANSLATE && k < dim) v = bc_wrap<VAR>(k, v + ((k == 0) ? dx[0] : ((k == 1) ? dx[1] : dx[2])));
+            sn(gs, k, ib) = v;
+        }
+        gsync();
+    }
+    if (flags & (MV_GLUE_II_X1 | MV_GLUE_IE_X2)) {
+        if (G.tid < dim) {
+            if (flags & MV_GLUE_II_X1) sn(gs, G.tid, ii) = gs->xend[G.tid];
+            else sn(gs, G.tid, ie) = gs->xend[3 + G.tid];
+        }
+        gsync();
+    }
+    double DeltaK = 0.0;
+    if (flags & MV_DK_OLD_ADD) DeltaK = link_DeltaK<VAR>(seg_old(gs), ii, ie, L);
+    const bool has_free = flags & (MV_FREE_NEXT | MV_FREE_PREV);
+    const int iend = (flags & MV_FREE_NEXT) ? ii : ie, ianc = (flags & MV_FREE_NEXT) ? ie : ii;
+    // beads that need Gaussians: interior + free end
+    const int g0 = (flags & MV_FREE_NEXT) ? ii : ii + 1, g1 = (flags & MV_FREE_PREV) ? ie : ie - 1;
+    if (!MT && type != MV_TRANSLATE) rng_gauss_fill<MT>(gs, &ctr, dim, g0, 1, g1 - g0 + 1);     // Philox: one pass per move
+    const int Nl = 31 - __clz(L);                                  // bisection: L = 2^Nl
+    const int nphase = (type == MV_BISECT) ? Nl + (has_free ? 1 : 0) : 1;
+    bool accept = true;
+    for (int ph = 0; ph < nphase; ++ph) {
+        const bool gate = (type == MV_BISECT) && has_free && ph == 0;          // free end of Move{Head,Tail}Bisection
+        const int lev = (type == MV_BISECT) ? ph + (has_free ? 0 : 1) : 0;     // 1..Nl
+        const int delta_ib = (type == MV_BISECT && !gate) ? (1 << (Nl - lev + 1)) : 2;
+        int b0, bs, nb;
+        if (type == MV_BISECT) {
+            if (gate) { b0 = iend; bs = 1; nb = 1; }
+            else { b0 = ii + (delta_ib >> 1); bs = delta_ib; nb = 1 << (lev - 1); }
+        } else { b0 = m0; bs = 1; nb = m1 - m0 + 1; }
+        if (MT) {      // the reference's draw order (Appendix A of SURVEY.md)
+            if (type == MV_BRIDGE) {
+                if (flags & MV_FREE_PREV) { rng_gauss_fill<MT>(gs, &ctr, dim, ie, 1, 1); rng_gauss_fill<MT>(gs, &ctr, dim, ii + 1, 1, L - 1); }
+                else rng_gauss_fill<MT>(gs, &ctr, dim, g0, 1, g1 - g0 + 1);
+            } else if (type == MV_BISECT) {
+                rng_gauss_fill<MT>(gs, &ctr, dim, b0, bs, nb);
             }
-            if (G.tid == 0) { gs->isopen = 1; gs->new_pc = 1; }
-            if (half == 1) commit(gs, ip0, ii + 1, ie); else commit(gs, ip0, ii, ie - 1);
-        } else {
-            if (G.tid < cP.dim) { gs->xend[G.tid] = so(gs, G.tid, cP.Nb); gs->xend[3 + G.tid] = so(gs, G.tid, cP.Nb); }
-            if (G.tid == 0) gs->new_pc = 0;
+        }
+        // ---- proposal
+        if (type == MV_BRIDGE || gate) {
+            if (G.tid < dim) {
+                const int k = G.tid;
+                if (has_free) {      // xnew = BC(unwrap(anchor) + sigma*g)    (vpi_mod.f90:619-645 / 758-785)
+                    double xold = so(gs, k, iend), g = sn(gs, k, iend), anc = sn(gs, k, ianc), base;
+                    if (flags & MV_FREE_NEXT) base = xold - wrap_lt<VAR>(k, xold - anc);
+                    else base = xold + wrap_lt<VAR>(k, anc - xold);
+                    sn(gs, k, iend) = bc_wrap<VAR>(k, base + sqrt((double)L * cP.dt) * g);
+                }
+                if (type == MV_BRIDGE) {      // Levy bridge ii -> ie (vpi_mod.f90:509-549)
+                    double pnext = sn(gs, k, ie), pprev = sn(gs, k, ii);
+                    for (int j = 1; j <= L - 1; ++j) {
+                        int ib = ii + j;
+                        double xold = so(gs, k, ib), g = sn(gs, k, ib);
+                        double xprev = xold + wrap_lt<VAR>(k, pprev - xold);
+                        double xnext = xold - wrap_lt<VAR>(k, xold - pnext);
+                        double sigma = sqrt((double)((float)(L - j) / (float)(L - j + 1)) * cP.dt);   // float32 ratio (Q15)
+                        double xmid = (xnext + xprev * (double)(L - j)) / (double)(L - j + 1);
+                        pprev = bc_wrap<VAR>(k, xmid + sigma * g);
+                        sn(gs, k, ib) = pprev;
+                    }
+                }
+            }
+            gsync();
+        } else if (type == MV_BISECT) {      // one bisection level (vpi_mod.f90:905-956)
+            double sigma = sqrt(0.5 * (0.5 * (double)delta_ib * cP.dt));
+            for (int i = G.tid; i < nb * dim; i += G.size) {
+                int j = div_dim(i), k = i - j * dim;
+                int iprev = ii + j * delta_ib, inext = iprev + delta_ib, icurr = (iprev + inext) >> 1;
+                double xold = so(gs, k, icurr), g = sn(gs, k, icurr);
+                double xprev = xold + wrap_lt<VAR>(k, sn(gs, k, iprev) - xold);
+                double xnext = xold - wrap_lt<VAR>(k, xold - sn(gs, k, inext));
+                sn(gs, k, icurr) = bc_wrap<VAR>(k, 0.5 * (xprev + xnext) + sigma * g);
+            }
             gsync();
         }
-    } else {
-        if (acc) {
-            bump(gs, C_ACC_CLOSE);
-            if (G.tid < cP.dim) { gs->xend[G.tid] = sn(gs, G.tid, cP.Nb); gs->xend[3 + G.tid] = sn(gs, G.tid, cP.Nb); }
-            if (G.tid == 0) { gs->isopen = 0; gs->end_pc = 1; }
-            if (half == 1) commit(gs, ip0, ii + 1, ie); else commit(gs, ip0, ii, ie - 1);
-        } else {
-            if (G.tid == 0) gs->end_pc = 0;
+        // ---- action
+        const double wf = (flags & MV_WFIRST_HALF) ? 0.5 : 1.0, wl = (flags & MV_WLAST_HALF) ? 0.5 : 1.0;
+        double S = eval_action<VAR>(gs, G, ip0, b0, bs, nb, (type == MV_BISECT) ? 1.0 : wf, (type == MV_BISECT) ? 1.0 : wl);
+        if (type != MV_BISECT) {
+            S += Sbase;
+            if (flags & MV_DK_OLD_ADD) S += DeltaK;
+            if (flags & MV_DK_NEW_SUB) S -= link_DeltaK<VAR>(seg_new(gs), ii, ie, L);
+        }
+        // ---- the Metropolis question (e.g. vpi_mod.f90:356-364): a uniform is consumed only if exp(-S)<1
+        if (!(S <= 0.0)) {
+            double e = exp(-S);
+            if (!(e >= 1.0)) {                     // NaN falls through: rejected after its draw (Q23)
+                double u = uniform<MT, VAR>(gs, ctr);
+                if (!(e >= u)) { accept = false; break; }
+            }
+        }
+        gsync();
+    }
+    if (accept) {
+        const int c0 = (type == MV_TRANSLATE) ? ii : m0, n = ((type == MV_TRANSLATE) ? ie : m1) - c0 + 1;
+        for (int i = G.tid; i < 3 * n; i += G.size) {
+            int k = (i >= n) + (i >= 2 * n), ib = c0 + (i - k * n);
+            if (k < dim) pth(gs, k, ip0, ib) = sn(gs, k, ib);
+        }
+    }
+    gsync();
+    *pctr = ctr;
+    return accept;
+}
+
+// ---------------------------------------------------------------- the 14 moves as descriptors
+PIGS_T __device__ __forceinline__ void TranslateChain(GS* gs, ull* pctr, int ip0) {              // vpi_mod.f90:313-379
+    if (run_move<MT, VAR>(gs, pctr, MV_TRANSLATE, ip0, 0, 2 * cP.Nb, 0, 2 * cP.Nb, 0.0)) bump(gs, C_ACC_CM);
+}
+PIGS_T __device__ __forceinline__ void TranslateHalfChain(GS* gs, ull* pctr, int half, int ip0) { // vpi_mod.f90:383-476
+    const int ibi = (half == 1) ? 0 : cP.Nb, ibf = ibi + cP.Nb;
+    // cut bead at full weight (Q21)
+    if (run_move<MT, VAR>(gs, pctr, MV_TRANSLATE | (half << 2), ip0, ibi, ibf, ibi, ibf, 0.0)) {
+        bump(gs, C_ACC_CM_HALF);
+        const int t = threadIdx.x & (cA.threads_per_chain - 1);
+        if (t < cP.dim) gs->xend[(half - 1) * 3 + t] = sn(gs, t, cP.Nb);
+        gsync();
+    }
+}
+PIGS_T __device__ __forceinline__ void Staging(GS* gs, ull* pctr, int L, int ip0) {              // vpi_mod.f90:480-578
+    ull ctr = *pctr;
+    int ii = draw_int<MT, VAR>(gs, ctr, 2 * cP.Nb - L + 1);
+    *pctr = ctr;
+    if (run_move<MT, VAR>(gs, pctr, MV_BRIDGE, ip0, ii, ii + L, ii + 1, ii + L - 1, 0.0)) bump(gs, C_ACC_BD);
+}
+PIGS_T __device__ __forceinline__ void StagingHalfChain(GS* gs, ull* pctr, int half, int L, int ip0) {   // vpi_mod.f90:1376-1491
+    ull ctr = *pctr;
+    int ii = draw_int<MT, VAR>(gs, ctr, cP.Nb - L + 1) + (half == 1 ? 0 : cP.Nb);
+    *pctr = ctr;
+    // interior beads never include the cut bead Nb, so xend(:,half) is unchanged on acceptance
+    if (run_move<MT, VAR>(gs, pctr, MV_BRIDGE | (half << 2), ip0, ii, ii + L, ii + 1, ii + L - 1, 0.0)) bump(gs, C_ACC_BD_HALF);
+}
+// MoveHead (vpi_mod.f90:582-720) for half == 0, MoveHeadHalfChain (:1495-1656) otherwise
+PIGS_T __device__ __forceinline__ void MoveHead(GS* gs, ull* pctr, int Lmax, int ip0, int half) {
+    ull ctr = *pctr;
+    int Ls = draw_int<MT, VAR>(gs, ctr, Lmax - 1) + 2;
+    *pctr = ctr;
+    int ii = (half == 2) ? cP.Nb : 0, ie = ii + Ls;
+    int fl = MV_BRIDGE | MV_FREE_NEXT | (half << 2) | (half == 2 ? MV_WFIRST_HALF : 0);     // cut bead weighs 1/2 (:1573-1577)
+    if (run_move<MT, VAR>(gs, pctr, fl, ip0, ii, ie, ii, ie - 1, 0.0)) {
+        bump(gs, half ? C_ACC_HEAD_HALF : C_ACC_HEAD);
+        if (half == 2) {       // the free end IS the cut bead
+            const int t = threadIdx.x & (cA.threads_per_chain - 1);
+            if (t < cP.dim) gs->xend[3 + t] = sn(gs, t, cP.Nb);
             gsync();
         }
     }
 }
-PIGS_T __device__ __noinline__ void Swap(GS* gs, ull* pctr, int Lmax, int iw0) {                // vpi_mod.f90:2270-2487
+// MoveTail (vpi_mod.f90:724-860) for half == 0, MoveTailHalfChain (:1660-1817) otherwise
+PIGS_T __device__ __forceinline__ void MoveTail(GS* gs, ull* pctr, int Lmax, int ip0, int half) {
+    ull ctr = *pctr;
+    int Ls = draw_int<MT, VAR>(gs, ctr, Lmax - 1) + 2;
+    *pctr = ctr;
+    int ie = (half == 1) ? cP.Nb : 2 * cP.Nb, ii = ie - Ls;
+    int fl = MV_BRIDGE | MV_FREE_PREV | (half << 2) | (half == 1 ? MV_WLAST_HALF : 0);      // (:1734-1738)
+    if (run_move<MT, VAR>(gs, pctr, fl, ip0, ii, ie, ii + 1, ie, 0.0)) {
+        bump(gs, half ? C_ACC_TAIL_HALF : C_ACC_TAIL);
+        if (half == 1) {
+            const int t = threadIdx.x & (cA.threads_per_chain - 1);
+            if (t < cP.dim) gs->xend[t] = sn(gs, t, cP.Nb);
+            gsync();
+        }
+    }
+}
+PIGS_T __device__ __forceinline__ void Bisection(GS* gs, ull* pctr, int level, int ip0) {        // vpi_mod.f90:864-998
+    ull ctr = *pctr;
+    int ii = draw_int<MT, VAR>(gs, ctr, 2 * cP.Nb - (1 << level) + 1), ie = ii + (1 << level);
+    *pctr = ctr;
+    if (run_move<MT, VAR>(gs, pctr, MV_BISECT, ip0, ii, ie, ii + 1, ie - 1, 0.0)) bump(gs, C_ACC_BD);
+}
+// MoveHeadBisection (vpi_mod.f90:1002-1184) when head, MoveTailBisection (:1188-1372) otherwise
+PIGS_T __device__ __forceinline__ void EndBisection(GS* gs, ull* pctr, int level, int ip0, bool head) {
+    ull ctr = *pctr;
+    int Nl = draw_int<MT, VAR>(gs, ctr, level - 1) + 2;
+    *pctr = ctr;
+    int ii = head ? 0 : 2 * cP.Nb - (1 << Nl), ie = ii + (1 << Nl);
+    if (run_move<MT, VAR>(gs, pctr, MV_BISECT | (head ? MV_FREE_NEXT : MV_FREE_PREV), ip0, ii, ie, head ? ii : ii + 1,
+                          head ? ie - 1 : ie, 0.0))
+        bump(gs, head ? C_ACC_HEAD : C_ACC_TAIL);
+}
+PIGS_T __device__ __forceinline__ int draw_even_Ls(GS* gs, ull& ctr, int Lmax) { return 2 * draw_int<MT, VAR>(gs, ctr, (Lmax - 2) / 2) + 2; }
+PIGS_T __device__ __forceinline__ int draw_half(GS* gs, ull& ctr) { int h = (int)(uniform<MT, VAR>(gs, ctr) * 2.0) + 1; return h > 2 ? 2 : h; }
+
+// OpenChain (vpi_mod.f90:1821-2076) when open, CloseChain (:2080-2266) otherwise
+PIGS_T static __device__ __noinline__ void OpenClose(GS* gs, ull* pctr, int Lmax, int ip0, bool open) {
+    const int t = threadIdx.x & (cA.threads_per_chain - 1);
+    ull ctr = *pctr;
+    int Ls = draw_even_Ls<MT, VAR>(gs, ctr, Lmax), half = draw_half<MT, VAR>(gs, ctr);
+    *pctr = ctr;
+    const int ii = (half == 1) ? cP.Nb - Ls : cP.Nb, ie = ii + Ls;
+    int fl = MV_BRIDGE | (half == 1 ? MV_WLAST_HALF : MV_WFIRST_HALF);
+    if (open) fl |= MV_DK_OLD_ADD | (half == 1 ? MV_FREE_PREV : MV_FREE_NEXT);
+    else fl |= MV_DK_NEW_SUB | (half == 1 ? MV_GLUE_IE_X2 : MV_GLUE_II_X1);
+    const int m0 = (half == 1) ? ii + 1 : ii, m1 = (half == 1) ? ie : ie - 1;
+    bool acc = run_move<MT, VAR>(gs, pctr, fl, ip0, ii, ie, m0, m1, open ? -cP.logCd : cP.logCd);
+    if (open) {
+        if (acc) {
+            bump(gs, C_ACC_OPEN);
+            if (t < cP.dim) {
+                gs->xend[t] = (half == 1) ? sn(gs, t, cP.Nb) : so(gs, t, cP.Nb);
+                gs->xend[3 + t] = (half == 1) ? so(gs, t, cP.Nb) : sn(gs, t, cP.Nb);
+            }
+            if (t == 0) { gs->isopen = 1; gs->new_pc = 1; }
+        } else {
+            if (t < cP.dim) { gs->xend[t] = so(gs, t, cP.Nb); gs->xend[3 + t] = so(gs, t, cP.Nb); }
+            if (t == 0) gs->new_pc = 0;
+        }
+    } else {
+        if (acc) {
+            bump(gs, C_ACC_CLOSE);
+            if (t < cP.dim) { gs->xend[t] = sn(gs, t, cP.Nb); gs->xend[3 + t] = sn(gs, t, cP.Nb); }
+            if (t == 0) { gs->isopen = 0; gs->end_pc = 1; }
+        } else {
+            if (t == 0) gs->end_pc = 0;
+        }
+    }
+    gsync();
+}
+PIGS_T static __device__ __noinline__ void Swap(GS* gs, ull* pctr, int Lmax, int iw0) {          // vpi_mod.f90:2270-2487
     const Grp G = grp();
     ull ctr = *pctr;
     if (G.tid == 0) gs->swap_acc = 0;
@@ -476,19 +458,15 @@ PIGS_T __device__ __noinline__ void Swap(GS* gs, ull* pctr, int Lmax, int iw0) {
         gsync();
         const double Sk = gs->bc[5];
         if (ug <= Sw / Sk) {
-            load_segment(gs, ik, ii, ie);
-            if (G.tid < cP.dim) sn(gs, G.tid, ie) = gs->xend[3 + G.tid];
-            gsync();
-            gauss_fill<MT, VAR>(gs, ctr, ii + 1, 1, Ls - 1);
-            stage_transform<VAR>(gs, ii, Ls, ie);
-            double S = eval_action<VAR>(gs, ik, ii + 1, 1, Ls - 1, 1.0, 1.0);
-            if (metropolis<MT, VAR>(gs, &ctr, S)) {
+            *pctr = ctr;
+            bool acc = run_move<MT, VAR>(gs, pctr, MV_BRIDGE | MV_GLUE_IE_X2, ik, ii, ie, ii + 1, ie - 1, 0.0);
+            ctr = *pctr;
+            if (acc) {
                 bump(gs, C_ACC_SWAP);
-                commit(gs, ik, ii + 1, ie - 1);
                 // exchange the second halves (vpi_mod.f90:2454-2464)
                 const int n = cP.Nb;                     // slices Nb+1..2Nb
-                for (int i = G.tid; i < cP.dim * n; i += G.size) {
-                    int k = i / n, ib = cP.Nb + 1 + (i - k * n);
+                for (int i = G.tid; i < 3 * n; i += G.size) {
+                    int k = (i >= n) + (i >= 2 * n), ib = cP.Nb + 1 + (i - k * n);
                     double a = pth(gs, k, iw0, ib), b = pth(gs, k, ik, ib);
                     pth(gs, k, iw0, ib) = b;
                     pth(gs, k, ik, ib) = a;
@@ -756,12 +734,11 @@ static __device__ __noinline__ void OBDM(const double* xend, double* nrho) {
 
 // ---------------------------------------------------------------- driver schedule
 PIGS_T __device__ __noinline__ void diag_sweep(GS* gs, ull* pctr, int istep, int skip0) {       // vpi.f90:329-366 / 412-439
-    const int S1 = cP.S - 1;
     if (istep % cP.CMFreq == 0) {
         for (int ip = 0; ip < cP.Np; ++ip) {
             if (ip == skip0) continue;
             bump(gs, C_TRY_CM);
-            TranslateRange<MT, VAR>(gs, pctr, ip, 0, S1, 0);
+            TranslateChain<MT, VAR>(gs, pctr, ip);
         }
     }
     for (int istag = 0; istag < cP.Nstag; ++istag) {
@@ -769,9 +746,9 @@ PIGS_T __device__ __noinline__ void diag_sweep(GS* gs, ull* pctr, int istep, int
             if (ip == skip0) continue;
             bump(gs, C_TRY_STAG);
             if (cP.sampling == 0) {
-                HeadMove<MT, VAR>(gs, pctr, cP.Lstag, ip, 0);
-                TailMove<MT, VAR>(gs, pctr, cP.Lstag, ip, 0);
-                StagingMove<MT, VAR>(gs, pctr, cP.Lstag, ip, 0);
+                MoveHead<MT, VAR>(gs, pctr, cP.Lstag, ip, 0);
+                MoveTail<MT, VAR>(gs, pctr, cP.Lstag, ip, 0);
+                Staging<MT, VAR>(gs, pctr, cP.Lstag, ip);
             } else {
                 EndBisection<MT, VAR>(gs, pctr, cP.Nlev, ip, true);
                 EndBisection<MT, VAR>(gs, pctr, cP.Nlev, ip, false);
@@ -813,13 +790,13 @@ PIGS_T __device__ __forceinline__ void mc_step(GS* gs, ull* pctr, int istep) {  
         for (int iobdm = 0; iobdm < cP.Nobdm; ++iobdm) {
             for (int j = 1; j <= 2; ++j) {
                 bump(gs, C_TRY_CM_HALF);
-                TranslateRange<MT, VAR>(gs, pctr, iw, j == 1 ? 0 : cP.Nb, j == 1 ? cP.Nb : 2 * cP.Nb, j);
+                TranslateHalfChain<MT, VAR>(gs, pctr, j, iw);
             }
             for (int j = 1; j <= 2; ++j) {
                 bump(gs, C_TRY_STAG_HALF);
-                HeadMove<MT, VAR>(gs, pctr, cP.Lstag, iw, j);
-                TailMove<MT, VAR>(gs, pctr, cP.Lstag, iw, j);
-                StagingMove<MT, VAR>(gs, pctr, cP.Lstag, iw, j);
+                MoveHead<MT, VAR>(gs, pctr, cP.Lstag, iw, j);
+                MoveTail<MT, VAR>(gs, pctr, cP.Lstag, iw, j);
+                StagingHalfChain<MT, VAR>(gs, pctr, j, cP.Lstag, iw);
             }
             if (cP.swapping) {
                 bump(gs, C_TRY_SWAP);
@@ -853,19 +830,18 @@ PIGS_T __device__ __forceinline__ void mc_step(GS* gs, ull* pctr, int istep) {  
 }
 
 PIGS_T __device__ __forceinline__ void do_move(GS* gs, ull* pctr, int move, int ip0, int half) {
-    const int S1 = cP.S - 1;
     switch (move) {
-    case 0: TranslateRange<MT, VAR>(gs, pctr, ip0, 0, S1, 0); break;
-    case 1: StagingMove<MT, VAR>(gs, pctr, cP.Lstag, ip0, 0); break;
-    case 2: HeadMove<MT, VAR>(gs, pctr, cP.Lstag, ip0, 0); break;
-    case 3: TailMove<MT, VAR>(gs, pctr, cP.Lstag, ip0, 0); break;
+    case 0: TranslateChain<MT, VAR>(gs, pctr, ip0); break;
+    case 1: Staging<MT, VAR>(gs, pctr, cP.Lstag, ip0); break;
+    case 2: MoveHead<MT, VAR>(gs, pctr, cP.Lstag, ip0, 0); break;
+    case 3: MoveTail<MT, VAR>(gs, pctr, cP.Lstag, ip0, 0); break;
     case 4: Bisection<MT, VAR>(gs, pctr, cP.Nlev, ip0); break;
     case 5: EndBisection<MT, VAR>(gs, pctr, cP.Nlev, ip0, true); break;
     case 6: EndBisection<MT, VAR>(gs, pctr, cP.Nlev, ip0, false); break;
-    case 7: TranslateRange<MT, VAR>(gs, pctr, ip0, half == 1 ? 0 : cP.Nb, half == 1 ? cP.Nb : 2 * cP.Nb, half); break;
-    case 8: StagingMove<MT, VAR>(gs, pctr, cP.Lstag, ip0, half); break;
-    case 9: HeadMove<MT, VAR>(gs, pctr, cP.Lstag, ip0, half); break;
-    case 10: TailMove<MT, VAR>(gs, pctr, cP.Lstag, ip0, half); break;
+    case 7: TranslateHalfChain<MT, VAR>(gs, pctr, half, ip0); break;
+    case 8: StagingHalfChain<MT, VAR>(gs, pctr, half, cP.Lstag, ip0); break;
+    case 9: MoveHead<MT, VAR>(gs, pctr, cP.Lstag, ip0, half); break;
+    case 10: MoveTail<MT, VAR>(gs, pctr, cP.Lstag, ip0, half); break;
     case 11:
         gsync();
         if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) gs->iworm0 = ip0;
