@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -27,7 +28,7 @@ static int fail(int code, const std::string& m) { g_err = m; return code; }
 struct pigs_ctx {
     pigs_params hp;
     DevParams P;
-    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32;
+    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32, prefetch = 1;
     size_t smem = 0;
     int nvec = 0;
     bool tables_set = false;
@@ -56,6 +57,7 @@ static SweepArgs base_args(pigs_ctx* h) {
     A.threads_per_chain = h->T;
     A.tshift = 0;
     while ((1 << A.tshift) < h->T) ++A.tshift;
+    A.prefetch = h->prefetch;
     return A;
 }
 static int launch(pigs_ctx* h, const SweepArgs& A) {
@@ -75,14 +77,19 @@ static int plan(pigs_ctx* h) {
     int T = p.threads_per_chain;
     if (T == 0) {
         // fill ~32 warps per SM: few chains -> wide groups, many chains -> one warp each
-        long long want = (long long)nsm * 1024 / (p.n_chains > 0 ? p.n_chains : 1);
+        int maxt0 = 1024;
+        CK(sweep_max_threads(h->mt, p.trap ? 3 : 0, &maxt0));
+        long long want = (long long)nsm * maxt0 / (p.n_chains > 0 ? p.n_chains : 1);
         T = 32;
         while (T * 2 <= want && T < 256) T *= 2;
     }
     if (T != 32 && T != 64 && T != 128 && T != 256 && T != 512) return fail(PIGS_E_ARG, "threads_per_chain must be 0,32,64,128,256,512");
     const size_t gbytes = (grp_smem_bytes(h->P.S, h->P.Np, T / 32) + 15) & ~(size_t)15;
     const size_t tabbytes = (size_t)(p.Nmax + 2) * sizeof(double);
-    int Gmax = 1024 / T;
+    int maxt = 1024;
+    CK(sweep_max_threads(h->mt, p.trap ? 3 : 0, &maxt));
+    if (T > maxt) return fail(PIGS_E_ARG, "threads_per_chain exceeds the kernel's launch bound");
+    int Gmax = maxt / T;
     if (T > 32 && Gmax > 16) Gmax = 16;        // named barriers 0..15
     int Gneed = (p.n_chains + nsm - 1) / nsm;  // chains per SM if spread evenly
     if (Gneed < 1) Gneed = 1;
@@ -148,6 +155,10 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     pigs_ctx* h = new pigs_ctx();
     h->hp = *p;
     h->mt = p->rng_mode == PIGS_RNG_MT_REPLAY ? 1 : 0;
+    {
+        const char* e = getenv("PIGS_PREFETCH");      // tuning knob (default on)
+        if (e) h->prefetch = atoi(e) != 0;
+    }
     DevParams& P = h->P;
     std::memset(&P, 0, sizeof P);
     P.dim = p->dim; P.Np = p->Np; P.Nb = p->Nb; P.S = 2 * p->Nb + 1;

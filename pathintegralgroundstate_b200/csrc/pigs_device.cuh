@@ -72,6 +72,7 @@ struct SweepArgs {
     int chain_only;      // >=0: only that chain (OP_UNIFORM/OP_GAUSS/OP_SEED)
     int seed;            // OP_SEED
     int groups_per_cta, threads_per_chain, tshift;   // T = 1 << tshift
+    int prefetch;        // issue L1 prefetches of a move's slices at move start
     int* accepted;       // OP_MOVE [n_chains]
     int* aux;            // OP_MOVE [n_chains]
     double* draws;       // OP_UNIFORM/OP_GAUSS [n]
@@ -366,94 +367,126 @@ __device__ __forceinline__ void rng_gauss_fill(GS* gs, unsigned long long* pctr,
 
 // ------------------------------------------------------------------ the pair sums of one bead-update
 // Per-lane partial sums for one displaced bead (UpdatePot, vpi_mod.f90:2660-2841,
-// UpdateWf, :2534-2656), old and new position against partner j:
-//   a[0] = PotNew-PotOld   a[1] = PsiNew-PsiOld
-//   a[2..4] = Fnew(k)      a[5..7] = Fold(k)
-// KIND: 0 interior even slice, 1 odd slice (Chin force term), 2 end slice (Jastrow).
+// UpdateWf, :2534-2656), old and new position against partner j.
+// KIND: 0 interior even slice   -> pot
+//       1 odd slice (Chin term) -> pot, Fnew(3), Fold(3)
+//       2 end slice (Jastrow)   -> pot, psi
+// Each class has its own loop with only its accumulators live (the kernel runs
+// at 64 registers per thread; ncu showed spills in a shared 8-accumulator loop).
 //
 // Branch-free: a partner outside the cutoff (or the moved particle itself) is
-// evaluated at r = rcut with weight 0, so the new and old positions of two
-// partners form four independent dependency chains the scheduler can overlap.
-template <int KIND, bool TRAP, bool VSM, bool WSM, bool IS_NEW>
-__device__ __forceinline__ void pair_one(const double* tV, const double* tW, bool valid, double x0, double x1, double x2,
-                                         double rx, double ry, double rz, double (&a)[8]) {
-    double d0 = x0 - rx, d1 = x1 - ry, d2 = x2 - rz;
+// evaluated at r = rcut with weight 0, so the new and old positions form
+// independent dependency chains the scheduler can overlap.
+struct PairGeom {
+    double d0, d1, d2, ir;
+    Lk k;
+    bool in_pot, in_wf;
+};
+template <int KIND, bool TRAP, bool IS_NEW>
+__device__ __forceinline__ PairGeom pair_geom(bool valid, double x0, double x1, double x2, double rx, double ry, double rz) {
+    PairGeom g;
+    g.d0 = x0 - rx; g.d1 = x1 - ry; g.d2 = x2 - rz;
     if (!TRAP) {
-        d0 = mimg(d0, cP.L[0], cP.Lh[0]);
-        d1 = mimg(d1, cP.L[1], cP.Lh[1]);
-        d2 = mimg(d2, cP.L[2], cP.Lh[2]);
+        g.d0 = mimg(g.d0, cP.L[0], cP.Lh[0]);
+        g.d1 = mimg(g.d1, cP.L[1], cP.Lh[1]);
+        g.d2 = mimg(g.d2, cP.L[2], cP.Lh[2]);
     }
-    double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+    double r2 = g.d0 * g.d0 + g.d1 * g.d1 + g.d2 * g.d2;
     // PBC: both positions cut at rcut (Q24).  Trap: UpdatePot cuts only the OLD
     // position (Q12), UpdateWf cuts nothing.
-    const bool in_pot = valid && (TRAP ? (IS_NEW || r2 <= cP.rcut2) : (r2 <= cP.rcut2));
-    const bool in_wf = TRAP ? valid : in_pot;
-    const bool any = (KIND == 2) ? in_wf : in_pot;
+    g.in_pot = valid && (TRAP ? (IS_NEW || r2 <= cP.rcut2) : (r2 <= cP.rcut2));
+    g.in_wf = TRAP ? valid : g.in_pot;
+    const bool any = (KIND == 2) ? g.in_wf : g.in_pot;
     double r2c = any ? r2 : cP.rcut2;
-    double ir = rsqrt(r2c);
-    double r = r2c * ir;
-    Lk k = lk_prep(r);
-    if (TRAP) k.i0 = min(k.i0, cP.Nmax - 1);
-    const double sgn = IS_NEW ? 1.0 : -1.0;
-    if (KIND == 1) {
-        double v, dv;
-        lk_val_d1<VSM>(tV, k, v, dv);
-        a[0] += in_pot ? sgn * v : 0.0;
-        double s = in_pot ? dv * ir : 0.0;
-        constexpr int o = IS_NEW ? 2 : 5;
-        a[o] += s * d0; a[o + 1] += s * d1; a[o + 2] += s * d2;
-    } else {
-        double v = lk_val<VSM>(tV, k);
-        a[0] += in_pot ? sgn * v : 0.0;
-    }
-    if (KIND == 2) {
-        double w = lk_val<WSM>(tW, k);
-        a[1] += in_wf ? sgn * w : 0.0;
-    }
-}
-
-template <int KIND, bool TRAP, bool VSM, bool WSM>
-__device__ __forceinline__ void pair_loop(const double* tV, const double* tW, const double* Rx, int ip0, int j0,
-                                          int jstride, const double (&xo)[3], const double (&xn)[3], double (&a)[8]) {
-    const double* Ry = Rx + cP.NpS;
-    const double* Rz = Ry + cP.NpS;
-#pragma unroll 1
-    for (int j = j0; j < cP.Np; j += jstride) {
-        const bool valid = (j != ip0);
-        double rx = Rx[j], ry = Ry[j], rz = Rz[j];
-        pair_one<KIND, TRAP, VSM, WSM, true>(tV, tW, valid, xn[0], xn[1], xn[2], rx, ry, rz, a);
-        pair_one<KIND, TRAP, VSM, WSM, false>(tV, tW, valid, xo[0], xo[1], xo[2], rx, ry, rz, a);
-    }
+    g.ir = rsqrt(r2c);
+    g.k = lk_prep(r2c * g.ir);
+    if (TRAP) g.k.i0 = min(g.k.i0, cP.Nmax - 1);
+    return g;
 }
 
 __device__ __forceinline__ int bead_kind(int ib) { return (ib == 0 || ib == 2 * cP.Nb) ? 2 : (ib & 1); }
 
-// lane-partial sums of one bead against partners j0, j0+jstride, ...; the lane
-// with add_self adds the one-body (trap) terms once.
+// interior even slice: returns the lane's share of PotNew-PotOld
+template <bool TRAP, bool VSM>
+__device__ __forceinline__ double pair_loop_even(const double* tV, const double* Rx, int ip0, int j0, int jstride,
+                                                 const double (&xo)[3], const double (&xn)[3]) {
+    const double* Ry = Rx + cP.NpS;
+    const double* Rz = Ry + cP.NpS;
+    double pot = 0.0;
+    // software pipeline: the next partner's coordinates are in flight while this one is evaluated
+    double nx = 0.0, ny = 0.0, nz = 0.0;
+    if (j0 < cP.Np) { nx = Rx[j0]; ny = Ry[j0]; nz = Rz[j0]; }
+#pragma unroll 1
+    for (int j = j0; j < cP.Np; j += jstride) {
+        const bool valid = (j != ip0);
+        const double rx = nx, ry = ny, rz = nz;
+        const int jn = j + jstride;
+        if (jn < cP.Np) { nx = Rx[jn]; ny = Ry[jn]; nz = Rz[jn]; }
+        PairGeom gn = pair_geom<0, TRAP, true>(valid, xn[0], xn[1], xn[2], rx, ry, rz);
+        PairGeom go = pair_geom<0, TRAP, false>(valid, xo[0], xo[1], xo[2], rx, ry, rz);
+        double vn = lk_val<VSM>(tV, gn.k), vo = lk_val<VSM>(tV, go.k);
+        pot += (gn.in_pot ? vn : 0.0) - (go.in_pot ? vo : 0.0);
+    }
+    return pot;
+}
+// end slice: pot and psi
 template <bool TRAP, bool VSM, bool WSM>
-__device__ __forceinline__ void bead_partial(const double* tV, const double* tW, const double* Rx, int ip0, int ib, int j0,
-                                             int jstride, bool add_self, const double (&xo)[3], const double (&xn)[3],
-                                             double (&a)[8]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = 0.0;
-    const int kind = bead_kind(ib);
-    if (TRAP && add_self) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {          // system_mod.f90:213-252
-            if (k < cP.dim) {
-                double ak = cP.a_ho[k], a2 = ak * ak, a4 = a2 * a2;
-                a[0] += 0.5 * xn[k] * xn[k] / a4 - 0.5 * xo[k] * xo[k] / a4;
-                if (kind == 1) { a[2 + k] += xn[k] / a4; a[5 + k] += xo[k] / a4; }
-                if (kind == 2) a[1] += -0.5 * (xn[k] / ak) * (xn[k] / ak) + 0.5 * (xo[k] / ak) * (xo[k] / ak);
-            }
+__device__ __forceinline__ void pair_loop_end(const double* tV, const double* tW, const double* Rx, int ip0, int j0,
+                                              int jstride, const double (&xo)[3], const double (&xn)[3], double& pot,
+                                              double& psi) {
+    const double* Ry = Rx + cP.NpS;
+    const double* Rz = Ry + cP.NpS;
+    double nx = 0.0, ny = 0.0, nz = 0.0;
+    if (j0 < cP.Np) { nx = Rx[j0]; ny = Ry[j0]; nz = Rz[j0]; }
+#pragma unroll 1
+    for (int j = j0; j < cP.Np; j += jstride) {
+        const bool valid = (j != ip0);
+        const double rx = nx, ry = ny, rz = nz;
+        const int jn = j + jstride;
+        if (jn < cP.Np) { nx = Rx[jn]; ny = Ry[jn]; nz = Rz[jn]; }
+        PairGeom gn = pair_geom<2, TRAP, true>(valid, xn[0], xn[1], xn[2], rx, ry, rz);
+        PairGeom go = pair_geom<2, TRAP, false>(valid, xo[0], xo[1], xo[2], rx, ry, rz);
+        double vn = lk_val<VSM>(tV, gn.k), vo = lk_val<VSM>(tV, go.k);
+        double wn = lk_val<WSM>(tW, gn.k), wo = lk_val<WSM>(tW, go.k);
+        pot += (gn.in_pot ? vn : 0.0) - (go.in_pot ? vo : 0.0);
+        psi += (gn.in_wf ? wn : 0.0) - (go.in_wf ? wo : 0.0);
+    }
+}
+// odd slice: pot and the moved particle's force at the new / old position (Q2)
+template <bool TRAP, bool VSM>
+__device__ __forceinline__ void pair_loop_odd(const double* tV, const double* Rx, int ip0, int j0, int jstride,
+                                              const double (&xo)[3], const double (&xn)[3], double& pot, double (&fn)[3],
+                                              double (&fo)[3]) {
+    const double* Ry = Rx + cP.NpS;
+    const double* Rz = Ry + cP.NpS;
+    double nx = 0.0, ny = 0.0, nz = 0.0;
+    if (j0 < cP.Np) { nx = Rx[j0]; ny = Ry[j0]; nz = Rz[j0]; }
+#pragma unroll 1
+    for (int j = j0; j < cP.Np; j += jstride) {
+        const bool valid = (j != ip0);
+        const double rx = nx, ry = ny, rz = nz;
+        const int jn = j + jstride;
+        if (jn < cP.Np) { nx = Rx[jn]; ny = Ry[jn]; nz = Rz[jn]; }
+        {
+            PairGeom g = pair_geom<1, TRAP, true>(valid, xn[0], xn[1], xn[2], rx, ry, rz);
+            double v, dv;
+            lk_val_d1<VSM>(tV, g.k, v, dv);
+            pot += g.in_pot ? v : 0.0;
+            double s = g.in_pot ? dv * g.ir : 0.0;
+            fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
+        }
+        {
+            PairGeom g = pair_geom<1, TRAP, false>(valid, xo[0], xo[1], xo[2], rx, ry, rz);
+            double v, dv;
+            lk_val_d1<VSM>(tV, g.k, v, dv);
+            pot -= g.in_pot ? v : 0.0;
+            double s = g.in_pot ? dv * g.ir : 0.0;
+            fo[0] += s * g.d0; fo[1] += s * g.d1; fo[2] += s * g.d2;
         }
     }
-    if (kind == 0) pair_loop<0, TRAP, VSM, WSM>(tV, tW, Rx, ip0, j0, jstride, xo, xn, a);
-    else if (kind == 1) pair_loop<1, TRAP, VSM, WSM>(tV, tW, Rx, ip0, j0, jstride, xo, xn, a);
-    else pair_loop<2, TRAP, VSM, WSM>(tV, tW, Rx, ip0, j0, jstride, xo, xn, a);
 }
 
-// DeltaS of UpdateAction from the eight reduced values
+// DeltaS of UpdateAction from the eight reduced values [pot, psi, Fnew(3), Fold(3)]
 // (GreenFunction opt 0, global_mod.f90:29-46).
 __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
     const int kind = bead_kind(ib);
@@ -463,23 +496,73 @@ __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
     double f2 = (v[2] * v[2] + v[3] * v[3] + v[4] * v[4]) - (v[5] * v[5] + v[6] * v[6] + v[7] * v[7]);
     return 4.0 * dt * (v[0] + dt * dt * f2 / 6.0) / 3.0;
 }
-// Whole-warp DeltaS of one bead from the per-lane partial sums, identical in
-// every lane; the reduction is specialised by bead class (1, 2 or 7 values).
-__device__ __forceinline__ double warp_dS(int ib, const double (&a)[8], int lane) {
+
+// One bead against partners j0, j0+jstride, ... by one warp.
+//  part == nullptr: all partners are covered by this warp -> returns DeltaS
+//                   (UpdateAction, vpi_mod.f90:2491-2530), identical in every lane;
+//  part != nullptr: the warp's partial sums are stored to part[0..7] for a later
+//                   combination with other warps (returns 0).
+// The lane with add_self adds the one-body (trap) terms once.
+template <bool TRAP, bool VSM, bool WSM>
+__device__ __forceinline__ double bead_eval(const double* tV, const double* tW, const double* Rx, int ip0, int ib, int j0,
+                                            int jstride, bool add_self, const double (&xo)[3], const double (&xn)[3],
+                                            int lane, double* part) {
     const int kind = bead_kind(ib);
     const double dt = cP.dt;
-    if (kind == 0) return (2.0 * dt / 3.0) * warp_sum(a[0]);
-    if (kind == 2) {
-        double v = warp_sum2(a[0], a[1], lane);
-        double t = (lane & 16) ? -v : (dt / 3.0) * v;
-        return t + shx(t, 16);
+    double pot = 0.0, psi = 0.0, fn[3] = {0.0, 0.0, 0.0}, fo[3] = {0.0, 0.0, 0.0};
+    if (TRAP && add_self) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {          // system_mod.f90:213-252
+            if (k < cP.dim) {
+                double ak = cP.a_ho[k], a2 = ak * ak, a4 = a2 * a2;
+                pot += 0.5 * xn[k] * xn[k] / a4 - 0.5 * xo[k] * xo[k] / a4;
+                if (kind == 1) { fn[k] += xn[k] / a4; fo[k] += xo[k] / a4; }
+                if (kind == 2) psi += -0.5 * (xn[k] / ak) * (xn[k] / ak) + 0.5 * (xo[k] / ak) * (xo[k] / ak);
+            }
+        }
     }
-    double v = warp_sum8(a, lane);
+    if (kind == 0) {
+        pot += pair_loop_even<TRAP, VSM>(tV, Rx, ip0, j0, jstride, xo, xn);
+        double v = warp_sum(pot);
+        if (!part) return (2.0 * dt / 3.0) * v;
+        if (lane < 8) part[lane] = (lane == 0) ? v : 0.0;
+        return 0.0;
+    }
+    if (kind == 2) {
+        pair_loop_end<TRAP, VSM, WSM>(tV, tW, Rx, ip0, j0, jstride, xo, xn, pot, psi);
+        double v = warp_sum2(pot, psi, lane);          // lanes 0..15: pot, lanes 16..31: psi
+        if (!part) {
+            double t = (lane & 16) ? -v : (dt / 3.0) * v;
+            return t + shx(t, 16);
+        }
+        if (lane == 0) part[0] = v;
+        if (lane == 16) part[1] = v;
+        if (lane >= 2 && lane < 8) part[lane] = 0.0;
+        return 0.0;
+    }
+    pair_loop_odd<TRAP, VSM>(tV, Rx, ip0, j0, jstride, xo, xn, pot, fn, fo);
+    const double a[8] = {pot, 0.0, fn[0], fn[1], fn[2], fo[0], fo[1], fo[2]};
+    double v = warp_sum8(a, lane);                      // quad q holds value q
     const int q = lane >> 2;
-    const double c = 4.0 * dt * dt * dt / 18.0;
-    double t = (q == 0) ? (4.0 * dt / 3.0) * v : ((q == 1) ? 0.0 : ((q < 5) ? c * v * v : -c * v * v));
-    t += shx(t, 4); t += shx(t, 8); t += shx(t, 16);
-    return t;
+    if (!part) {
+        const double c = 4.0 * dt * dt * dt / 18.0;
+        double t = (q == 0) ? (4.0 * dt / 3.0) * v : ((q == 1) ? 0.0 : ((q < 5) ? c * v * v : -c * v * v));
+        t += shx(t, 4); t += shx(t, 8); t += shx(t, 16);
+        return t;
+    }
+    if ((lane & 3) == 0) part[q] = v;
+    return 0.0;
+}
+
+// L1 prefetch of the slices a move is going to read (other particles of the
+// displaced beads' time slices): issued at move start so the HBM/L2 latency
+// overlaps the proposal generation (ncu: 31% of stall samples sat on the first
+// use of these loads).
+__device__ __forceinline__ void prefetch_slices(const double* path, int b0, int nslice, int tid, int nthreads) {
+    const int lines_per_slice = (3 * cP.NpS * 8 + 127) >> 7;
+    const char* base = reinterpret_cast<const char*>(path + (size_t)b0 * 3 * cP.NpS);
+    const int nlines = nslice * lines_per_slice;      // slices are contiguous
+    for (int i = tid; i < nlines; i += nthreads) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + ((size_t)i << 7)));
 }
 
 }  // namespace pigs

@@ -12,6 +12,7 @@ cudaError_t launch_sweep(int mt, int var, const DevParams& P, const SweepArgs& A
                          cudaStream_t st);
 cudaError_t sweep_set_smem(int mt, int var, size_t smem);
 cudaError_t sweep_occupancy(int mt, int var, int block, size_t smem, int* ctas_per_sm);
+cudaError_t sweep_max_threads(int mt, int var, int* n);      // the instantiation's __launch_bounds__
 
 // unit kernels (pigs_unit.cu)
 enum UnitOp { U_LOCAL_ENERGY = 0, U_THERM_ENERGY = 1, U_PAIR_CORR = 2, U_SOFK = 3, U_OBDM = 4 };

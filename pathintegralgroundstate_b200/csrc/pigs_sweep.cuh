@@ -77,18 +77,15 @@ __device__ __forceinline__ double eval_action(GS* gs, const Grp& G, int ip0, int
         int m = task, s = 0;
         if (split > 1) { m = task / split; s = task - m * split; }
         const int ib = b0 + m * bstride;
-        double xo[3], xn[3], a[8];
+        double xo[3], xn[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) { xo[k] = so(gs, k, ib); xn[k] = sn(gs, k, ib); }
-        bead_partial<PIGS_TRAP, PIGS_VSM, PIGS_WSM>(tV, tW, slice(gs, ib), ip0, ib, s * 32 + G.lane, 32 * split,
-                                                   (s == 0) && (G.lane == 0), xo, xn, a);
+        double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM>(tV, tW, slice(gs, ib), ip0, ib, s * 32 + G.lane, 32 * split,
+                                                           (s == 0) && (G.lane == 0), xo, xn, G.lane,
+                                                           (split == 1) ? nullptr : part + task * 8);
         if (split == 1) {
-            double t = warp_dS(ib, a, G.lane);
             double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
             Sw += w * t;
-        } else {
-            double v = warp_sum8(a, G.lane);
-            if ((G.lane & 3) == 0) part[task * 8 + (G.lane >> 2)] = v;
         }
     }
     if (nw == 1) return Sw;
@@ -158,6 +155,7 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
     const int half = (flags & MV_HALF_MASK) >> 2;
     const int L = ie - ii;
     const int dim = cP.dim;
+    if (cA.prefetch) prefetch_slices(gs->path, (type == MV_TRANSLATE) ? ii : m0, ((type == MV_TRANSLATE) ? ie : m1) - ((type == MV_TRANSLATE) ? ii : m0) + 1, G.tid, G.size);
     if (half) {
         if (G.tid < dim) pth(gs, G.tid, ip0, cP.Nb) = gs->xend[(half - 1) * 3 + G.tid];
         gsync();

@@ -23,6 +23,7 @@ cudaError_t launch_sweep(int mt, int var, const DevParams& P, const SweepArgs& A
 }
 cudaError_t sweep_set_smem(int mt, int var, size_t smem) { return pick(mt, var)(1, nullptr, nullptr, 0, 0, smem, 0, nullptr); }
 cudaError_t sweep_occupancy(int mt, int var, int block, size_t smem, int* n) { return pick(mt, var)(2, nullptr, nullptr, 0, block, smem, 0, n); }
+cudaError_t sweep_max_threads(int mt, int var, int* n) { return pick(mt, var)(3, nullptr, nullptr, 0, 0, 0, 0, n); }
 
 // ---------------------------------------------------------------- estimators on caller data
 // one CTA (= one chain group of 128 threads) per configuration
@@ -87,12 +88,11 @@ __global__ void __launch_bounds__(128) k_update_action(int n, const double* Rsoa
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (int e = w; e < n; e += nw) {
-        double xo[3] = {0, 0, 0}, xn[3] = {0, 0, 0}, a[8];
+        double xo[3] = {0, 0, 0}, xn[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 3; ++k) if (k < cP.dim) { xo[k] = xold[e * cP.dim + k]; xn[k] = xnew[e * cP.dim + k]; }
-        bead_partial<TRAP, false, false>(cP.vtab, cP.logwf, Rsoa + (size_t)e * 3 * cP.NpS, ip[e] - 1, ib[e], lane, 32,
-                                         lane == 0, xo, xn, a);
-        double t = warp_dS(ib[e], a, lane);
+        double t = bead_eval<TRAP, false, false>(cP.vtab, cP.logwf, Rsoa + (size_t)e * 3 * cP.NpS, ip[e] - 1, ib[e], lane, 32,
+                                                 lane == 0, xo, xn, lane, nullptr);
         if (lane == 0) dS[e] = t;
     }
 }

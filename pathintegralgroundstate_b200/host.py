@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpigs_cuda.so")
+# PIGS_LIB selects an alternative build of the same library (tuning experiments only)
+LIB_PATH = os.environ.get("PIGS_LIB") or os.path.join(_HERE, "libpigs_cuda.so")
 
 PIGS_RNG_PHILOX, PIGS_RNG_MT_REPLAY = 0, 1
 MOVES = dict(
