@@ -170,6 +170,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
         bool used = k < p->dim && !p->trap;
         P.L[k] = used ? p->Lbox[k] : 1e300;
         P.Lh[k] = used ? 0.5 * p->Lbox[k] : 0.5e300;          // LboxHalf, vpi.f90:118
+        P.invL[k] = used ? 1.0 / p->Lbox[k] : 0.0;
         P.qbin[k] = used ? 2.0 * std::acos(-1.0) / p->Lbox[k] : 0.0;   // vpi.f90:119
         P.a_ho[k] = k < p->dim ? p->a_ho[k] : 1.0;
     }

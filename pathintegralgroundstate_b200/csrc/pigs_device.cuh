@@ -27,6 +27,14 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// partner-loop unroll factor of the hot loops (register budget permitting)
+#ifndef PIGS_UNROLL
+#define PIGS_UNROLL 1
+#endif
+#define PIGS_STR2(x) #x
+#define PIGS_STR(x) PIGS_STR2(x)
+#define PIGS_PRAGMA_UNROLL _Pragma(PIGS_STR(unroll PIGS_UNROLL))
+
 namespace pigs {
 
 constexpr int NE = 12;      // energy sums
@@ -44,7 +52,7 @@ struct DevParams {
     int dim, Np, Nb, S, NpS, Nmax, Nbin, Nk, Npw;
     int trap, sampling, Lstag, Nlev, Nstag, Nobdm, swapping, CMFreq;
     int n_chains;
-    double L[3], Lh[3], qbin[3], a_ho[3];
+    double L[3], Lh[3], invL[3], qbin[3], a_ho[3];
     double rcut2, dr, inv_dr, rbin, dt, delta_cm, CWorm, density, pi, logCd;
     unsigned long long seed;
     const double* logwf;      // (0:Nmax+1) in global memory
@@ -141,10 +149,32 @@ template <> struct VarTraits<1> { static constexpr bool TRAP = false, VSM = true
 template <> struct VarTraits<2> { static constexpr bool TRAP = false, VSM = true,  WSM = true;  };
 template <> struct VarTraits<3> { static constexpr bool TRAP = true,  VSM = false, WSM = false; };
 
+// Table reads with the address space known at compile time: the staged copies
+// sit at the start of dynamic shared memory (VTable first, then LogWF), so the
+// loads are LDS with no generic-address detour.  WHICH: 0 VTable, 1 LogWF.
+template <bool SM, int WHICH, bool VSM_FIRST>
+__device__ __forceinline__ double tab(int i) {
+    if (SM) {
+        extern __shared__ __align__(16) double pigs_smem_base[];
+        const int off = (WHICH == 1 && VSM_FIRST) ? cP.Nmax + 2 : 0;
+        return pigs_smem_base[off + i];
+    }
+    return __ldg((WHICH == 0 ? cP.vtab : cP.logwf) + i);
+}
 template <bool SM>
 __device__ __forceinline__ double tld(const double* t, int i) {
     if (SM) return t[i];
     return __ldg(t + i);
+}
+// 1/sqrt(x) for normal positive x: hardware seed (MUFU.RSQ64H, ~20 bits) and one
+// cubically convergent step -- 5 FP64 issue slots, no slow-path call inside the
+// partner loop.  Relative error < 2^-52 * 2.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);                 // 1 - x y^2
+    double p = fma(0.375, e, 0.5);
+    return fma(y * e, p, y);                        // y (1 + e/2 + 3e^2/8)
 }
 
 // Interpolate(opt,...) of interpolate.f90:1-45, fast form for the hot loop:
@@ -165,13 +195,13 @@ __device__ __forceinline__ Lk lk_prep(double r) {
     k.a2 = cP.dr - k.a1;
     return k;
 }
-template <bool SM>
-__device__ __forceinline__ double lk_val(const double* F, const Lk& k) {   // opt 0
-    return (k.a1 * tld<SM>(F, k.i0 + 1) + k.a2 * tld<SM>(F, k.i0)) * cP.inv_dr;
+template <bool SM, int WHICH, bool VF>
+__device__ __forceinline__ double lk_val(const Lk& k) {   // opt 0
+    return (k.a1 * tab<SM, WHICH, VF>(k.i0 + 1) + k.a2 * tab<SM, WHICH, VF>(k.i0)) * cP.inv_dr;
 }
-template <bool SM>
-__device__ __forceinline__ void lk_val_d1(const double* F, const Lk& k, double& v, double& d1) {   // opt 0 and 1
-    double fm = tld<SM>(F, k.i0 - 1), f0 = tld<SM>(F, k.i0), f1 = tld<SM>(F, k.i0 + 1), f2 = tld<SM>(F, k.i0 + 2);
+template <bool SM, int WHICH, bool VF>
+__device__ __forceinline__ void lk_val_d1(const Lk& k, double& v, double& d1) {   // opt 0 and 1
+    double fm = tab<SM, WHICH, VF>(k.i0 - 1), f0 = tab<SM, WHICH, VF>(k.i0), f1 = tab<SM, WHICH, VF>(k.i0 + 1), f2 = tab<SM, WHICH, VF>(k.i0 + 2);
     double Fc = k.a1 * f1 + k.a2 * f0;
     double Fb = k.a1 * f0 + k.a2 * fm;
     double Fa = k.a1 * f2 + k.a2 * f1;
@@ -220,6 +250,15 @@ __device__ __forceinline__ double mimg_lt_first(double d, double L, double Lh) {
     if (d < -Lh) d += L;
     if (d > Lh) d -= L;
     return d;
+}
+
+// Hot-loop form: d - L*rint(d/L) with rint() by the 2^52 trick (3 FP64 issue
+// slots instead of 4 + 4 selects).  Identical to mimg() for |d| < 1.5 L except
+// exactly at |d| = L/2, where either image gives the same r^2.
+__device__ __forceinline__ double mimg_fast(double d, double L, double invL) {
+    const double MAGIC = 6755399441055744.0;
+    double q = fma(d, invL, MAGIC) - MAGIC;
+    return fma(-q, L, d);
 }
 
 // ------------------------------------------------------------------ warp reductions
@@ -387,9 +426,9 @@ __device__ __forceinline__ PairGeom pair_geom(bool valid, double x0, double x1, 
     PairGeom g;
     g.d0 = x0 - rx; g.d1 = x1 - ry; g.d2 = x2 - rz;
     if (!TRAP) {
-        g.d0 = mimg(g.d0, cP.L[0], cP.Lh[0]);
-        g.d1 = mimg(g.d1, cP.L[1], cP.Lh[1]);
-        g.d2 = mimg(g.d2, cP.L[2], cP.Lh[2]);
+        g.d0 = mimg_fast(g.d0, cP.L[0], cP.invL[0]);
+        g.d1 = mimg_fast(g.d1, cP.L[1], cP.invL[1]);
+        g.d2 = mimg_fast(g.d2, cP.L[2], cP.invL[2]);
     }
     double r2 = g.d0 * g.d0 + g.d1 * g.d1 + g.d2 * g.d2;
     // PBC: both positions cut at rcut (Q24).  Trap: UpdatePot cuts only the OLD
@@ -398,7 +437,7 @@ __device__ __forceinline__ PairGeom pair_geom(bool valid, double x0, double x1, 
     g.in_wf = TRAP ? valid : g.in_pot;
     const bool any = (KIND == 2) ? g.in_wf : g.in_pot;
     double r2c = any ? r2 : cP.rcut2;
-    g.ir = rsqrt(r2c);
+    g.ir = rsqrt_pos(r2c);
     g.k = lk_prep(r2c * g.ir);
     if (TRAP) g.k.i0 = min(g.k.i0, cP.Nmax - 1);
     return g;
@@ -416,7 +455,7 @@ __device__ __forceinline__ double pair_loop_even(const double* tV, const double*
     // software pipeline: the next partner's coordinates are in flight while this one is evaluated
     double nx = 0.0, ny = 0.0, nz = 0.0;
     if (j0 < cP.Np) { nx = Rx[j0]; ny = Ry[j0]; nz = Rz[j0]; }
-#pragma unroll 1
+PIGS_PRAGMA_UNROLL
     for (int j = j0; j < cP.Np; j += jstride) {
         const bool valid = (j != ip0);
         const double rx = nx, ry = ny, rz = nz;
@@ -424,7 +463,7 @@ __device__ __forceinline__ double pair_loop_even(const double* tV, const double*
         if (jn < cP.Np) { nx = Rx[jn]; ny = Ry[jn]; nz = Rz[jn]; }
         PairGeom gn = pair_geom<0, TRAP, true>(valid, xn[0], xn[1], xn[2], rx, ry, rz);
         PairGeom go = pair_geom<0, TRAP, false>(valid, xo[0], xo[1], xo[2], rx, ry, rz);
-        double vn = lk_val<VSM>(tV, gn.k), vo = lk_val<VSM>(tV, go.k);
+        double vn = lk_val<VSM, 0, VSM>(gn.k), vo = lk_val<VSM, 0, VSM>(go.k);
         pot += (gn.in_pot ? vn : 0.0) - (go.in_pot ? vo : 0.0);
     }
     return pot;
@@ -438,7 +477,7 @@ __device__ __forceinline__ void pair_loop_end(const double* tV, const double* tW
     const double* Rz = Ry + cP.NpS;
     double nx = 0.0, ny = 0.0, nz = 0.0;
     if (j0 < cP.Np) { nx = Rx[j0]; ny = Ry[j0]; nz = Rz[j0]; }
-#pragma unroll 1
+PIGS_PRAGMA_UNROLL
     for (int j = j0; j < cP.Np; j += jstride) {
         const bool valid = (j != ip0);
         const double rx = nx, ry = ny, rz = nz;
@@ -446,8 +485,8 @@ __device__ __forceinline__ void pair_loop_end(const double* tV, const double* tW
         if (jn < cP.Np) { nx = Rx[jn]; ny = Ry[jn]; nz = Rz[jn]; }
         PairGeom gn = pair_geom<2, TRAP, true>(valid, xn[0], xn[1], xn[2], rx, ry, rz);
         PairGeom go = pair_geom<2, TRAP, false>(valid, xo[0], xo[1], xo[2], rx, ry, rz);
-        double vn = lk_val<VSM>(tV, gn.k), vo = lk_val<VSM>(tV, go.k);
-        double wn = lk_val<WSM>(tW, gn.k), wo = lk_val<WSM>(tW, go.k);
+        double vn = lk_val<VSM, 0, VSM>(gn.k), vo = lk_val<VSM, 0, VSM>(go.k);
+        double wn = lk_val<WSM, 1, VSM>(gn.k), wo = lk_val<WSM, 1, VSM>(go.k);
         pot += (gn.in_pot ? vn : 0.0) - (go.in_pot ? vo : 0.0);
         psi += (gn.in_wf ? wn : 0.0) - (go.in_wf ? wo : 0.0);
     }
@@ -461,7 +500,7 @@ __device__ __forceinline__ void pair_loop_odd(const double* tV, const double* Rx
     const double* Rz = Ry + cP.NpS;
     double nx = 0.0, ny = 0.0, nz = 0.0;
     if (j0 < cP.Np) { nx = Rx[j0]; ny = Ry[j0]; nz = Rz[j0]; }
-#pragma unroll 1
+PIGS_PRAGMA_UNROLL
     for (int j = j0; j < cP.Np; j += jstride) {
         const bool valid = (j != ip0);
         const double rx = nx, ry = ny, rz = nz;
@@ -470,7 +509,7 @@ __device__ __forceinline__ void pair_loop_odd(const double* tV, const double* Rx
         {
             PairGeom g = pair_geom<1, TRAP, true>(valid, xn[0], xn[1], xn[2], rx, ry, rz);
             double v, dv;
-            lk_val_d1<VSM>(tV, g.k, v, dv);
+            lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
             pot += g.in_pot ? v : 0.0;
             double s = g.in_pot ? dv * g.ir : 0.0;
             fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
@@ -478,7 +517,7 @@ __device__ __forceinline__ void pair_loop_odd(const double* tV, const double* Rx
         {
             PairGeom g = pair_geom<1, TRAP, false>(valid, xo[0], xo[1], xo[2], rx, ry, rz);
             double v, dv;
-            lk_val_d1<VSM>(tV, g.k, v, dv);
+            lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
             pot -= g.in_pot ? v : 0.0;
             double s = g.in_pot ? dv * g.ir : 0.0;
             fo[0] += s * g.d0; fo[1] += s * g.d1; fo[2] += s * g.d2;

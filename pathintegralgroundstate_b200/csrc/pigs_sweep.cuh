@@ -29,6 +29,12 @@ namespace pigs {
 
 typedef unsigned long long ull;
 
+// (measured: making the action evaluation a real call costs 35% -- call-site spills;
+// it stays inlined into the move engine)
+
+#ifndef PIGS_EVAL_INLINE
+#define PIGS_EVAL_INLINE __forceinline__
+#endif
 #define PIGS_T template <bool MT, int VAR>
 #define PIGS_TRAP (VarTraits<VAR>::TRAP)
 #define PIGS_VSM (VarTraits<VAR>::VSM)
@@ -56,8 +62,9 @@ __device__ __forceinline__ int div_dim(int i) {          // i / cP.dim for dim i
 // (split = 1) and reduces to DeltaS with shuffles only; with fewer beads the
 // partners of a bead are divided over `split` warps and combined through smem.
 template <int VAR>
-__device__ __forceinline__ double eval_action(GS* gs, const Grp& G, int ip0, int b0, int bstride, int nb, double wfirst,
-                                              double wlast) {
+static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, int bstride, int nb, double wfirst,
+                                                      double wlast) {
+    const Grp G = grp();
     if (G.tid == 0) {
         for (int m = 0; m < nb; ++m) gs->cnt[C_UPD_EVEN + bead_kind(b0 + m * bstride)] += 1;
     }
@@ -250,7 +257,7 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
         }
         // ---- action
         const double wf = (flags & MV_WFIRST_HALF) ? 0.5 : 1.0, wl = (flags & MV_WLAST_HALF) ? 0.5 : 1.0;
-        double S = eval_action<VAR>(gs, G, ip0, b0, bs, nb, (type == MV_BISECT) ? 1.0 : wf, (type == MV_BISECT) ? 1.0 : wl);
+        double S = eval_action<VAR>(gs, ip0, b0, bs, nb, (type == MV_BISECT) ? 1.0 : wf, (type == MV_BISECT) ? 1.0 : wl);
         if (type != MV_BISECT) {
             S += Sbase;
             if (flags & MV_DK_OLD_ADD) S += DeltaK;
@@ -632,18 +639,18 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
             }
             double r2 = d0 * d0 + d1 * d1 + d2 * d2;
             if (PIGS_TRAP || r2 <= cP.rcut2) {
-                double ir = rsqrt(r2);
+                double ir = rsqrt_pos(r2);
                 double r = r2 * ir;
                 Lk k = lk_prep(r);
                 if (PIGS_TRAP) k.i0 = min(k.i0, cP.Nmax - 1);
                 if (odd) {
                     double v, dv;
-                    lk_val_d1<PIGS_VSM>(tV, k, v, dv);
+                    lk_val_d1<PIGS_VSM, 0, PIGS_VSM>(k, v, dv);
                     pot += v;
                     double q = dv * ir;
                     F[0] += q * d0; F[1] += q * d1; F[2] += q * d2;
                 } else {
-                    pot += lk_val<PIGS_VSM>(tV, k);
+                    pot += lk_val<PIGS_VSM, 0, PIGS_VSM>(k);
                 }
             }
         }
