@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- MC bead-updates/sec of the PIGS hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[2] -- liquid He-4, N = 256
+atoms at rho = 0.365 sigma^-3, 2M = 30 beads, Chin action, bisection moves,
+worm algorithm on (CWorm = 0.5, Nobdm = 10, swap), mixed + thermodynamic
+energies, g(r), S(k) and OBDM estimators -- run as `chains` independent Markov
+chains per GPU (weak scaling: the per-GPU chain count is fixed).  One "step" =
+one Monte-Carlo block of `mc_steps_per_block` driver steps (vpi.f90:297-475) on
+every chain, followed by the block-boundary reduction (all-reduce for N > 1).
+One bead-update = one UpdateAction evaluation (vpi_mod.f90:2491), counted on
+the device per slice class.
+
+Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the
+library's stream, inputs resident in HBM; `e2e` adds the host<->device copies
+of the chains' state through the C ABI with host buffers.  The reference arm
+times the CPU oracle (the C++ restatement of the Fortran reference -- no Fortran
+compiler exists in this image) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MC bead-updates/sec, liquid He-4 N=256"
+UNIT = "bead-updates/s"
+WORKLOAD = "C3"
+CHAINS_PER_GPU = 2368          # 148 SMs x 16 chain groups
+MC_STEPS_PER_BLOCK = 4
+SEED = 20260101
+
+
+def oracle_cfg(cfg):
+    c = dict(cfg)
+    for k in ("trap", "swapping", "wf_table", "v_table", "crystal"):
+        if k in c:
+            c[k] = int(bool(c[k]))
+    c.pop("tables", None)
+    return c
+
+
+# ------------------------------------------------------------------ CPU oracle legs (the only oracle/ users here)
+def _oracle_worker(cfg, P0, xe0, seed, native, st):
+    from oracle.pigs_oracle import Oracle
+    o = Oracle(oracle_cfg(cfg), native=native)
+    o.fill_tables()
+    o.set_state(P0, xe0, 0, 0)
+    o.sgrnd(seed)
+    while True:
+        st["start"].wait()
+        if st["stop"]:
+            return
+        b, _, _, _ = o.run_block(st["nstep"])        # ctypes releases the GIL: the cores run concurrently
+        st["done"].append(sum(b["bead_updates"]))
+        st["end"].wait()
+
+
+class OraclePool:
+    """one independent reference chain per host core (the reference's only form of parallelism)"""
+
+    def __init__(self, cfg, cores, native=False):
+        from pathintegralgroundstate_b200.workloads import synthetic_paths
+        self.cores = cores
+        P, xe = synthetic_paths(cfg, cores, seed=SEED)
+        self.st = dict(start=threading.Barrier(cores + 1), end=threading.Barrier(cores + 1), stop=False, nstep=1, done=[])
+        self.threads = [threading.Thread(target=_oracle_worker, args=(cfg, P[i], xe[i], 1982 + i, native, self.st),
+                                         daemon=True) for i in range(cores)]
+        for t in self.threads:
+            t.start()
+
+    def step(self, nstep=1):
+        """every core advances its chain by nstep MC steps; returns (bead_updates, seconds)"""
+        self.st["nstep"] = nstep
+        self.st["done"].clear()
+        t0 = time.perf_counter()
+        self.st["start"].wait()
+        self.st["end"].wait()
+        dt = time.perf_counter() - t0
+        return sum(self.st["done"]), dt
+
+    def close(self):
+        self.st["stop"] = True
+        self.st["start"].wait()
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(cfg, budget_s=12.0):
+    cores = host_cores()
+    pool = OraclePool(cfg, cores)
+    pool.step(1)
+    n_tot, t_tot, nblk = 0, 0.0, 0
+    while t_tot < budget_s:
+        n, dt = pool.step(1)
+        n_tot += n
+        t_tot += dt
+        nblk += 1
+    pool.close()
+    return dict(value=n_tot / t_tot, unit=UNIT, cores=cores, kind="port",
+                sample=f"{cores} independent {WORKLOAD} chains (one per core, g++ -O2 C++ restatement of the Fortran "
+                       f"reference; gfortran unavailable in image), {nblk} MC steps each, {t_tot:.1f} s")
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    pool = OraclePool(cfg, cores)
+    for _ in range(max(args.warmup, 1)):
+        pool.step(1)
+    n_tot, t_tot = 0, 0.0
+    for _ in range(args.steps):
+        n, dt = pool.step(1)
+        n_tot += n
+        t_tot += dt
+    pool.close()
+    v = n_tot / t_tot
+    sample = (f"{cores} independent {WORKLOAD} chains, one per host core, 1 MC step per bench step; C++ restatement of "
+              f"the Fortran reference (oracle/, g++ -O2): no Fortran compiler in this image")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "Np": cfg["Np"], "Nb": cfg["Nb"], "chains": cores, "mc_steps_per_step": 1},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {getattr(nv, n): n for n in dir(nv) if n.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, n), int)}
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, n in names.items():
+                    if bit and (r & bit) and n not in ("nvmlClocksThrottleReasonAll", "nvmlClocksThrottleReasonNone", "nvmlClocksThrottleReasonGpuIdle"):
+                        self.reasons.add(n.replace("nvmlClocksThrottleReason", ""))
+                time.sleep(0.1)
+        except Exception as e:       # clocks are evidence, not a dependency
+            self.reasons.add(f"sampler-error:{type(e).__name__}")
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------ the GPU arm
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from pathintegralgroundstate_b200 import PigsCuda, measure_fp64_peak
+    from pathintegralgroundstate_b200.multi_gpu import init_process_group, shard_chains, chain_seed, _CudaArray
+    from pathintegralgroundstate_b200.workloads import synthetic_paths, flops_per_bead_update
+
+    rank, local, world = init_process_group("nccl")
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    n_chains = args.chains
+    first, _ = shard_chains(n_chains * world, rank, world)
+
+    sim = PigsCuda(cfg, n_chains=n_chains, rng="philox", seed=chain_seed(SEED, first), device=local)
+    sim.fill_tables("hfdb")
+    P, xe = synthetic_paths(cfg, n_chains, seed=SEED + 7919 * rank)
+    # pinned host buffers of the chains' state (the e2e leg copies them every step)
+    hP = torch.from_numpy(P).pin_memory()
+    hX = torch.from_numpy(xe).pin_memory()
+    hO = torch.zeros(n_chains, dtype=torch.int32).pin_memory()
+    hW = torch.zeros(n_chains, dtype=torch.int32).pin_memory()
+    del P, xe
+    sim.set_state_all(hP.numpy(), hX.numpy(), hO.numpy(), hW.numpy())
+    lib_stream = torch.cuda.ExternalStream(sim.stream(), device=local)
+    ptr, nvec = sim.block_vector()
+    vec_t = torch.as_tensor(_CudaArray(ptr, nvec), device=f"cuda:{local}")
+    nstep = args.mc_steps
+
+    def one_step():
+        sim.run_block(nstep, sync=False)
+        if world > 1:
+            sim.sync()
+            dist.all_reduce(vec_t, op=dist.ReduceOp.SUM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        sim.sync()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events on the library's stream, max over ranks
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = sim.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, upd_cls = 0.0, np.zeros(3)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(lib_stream)
+    for _ in range(args.steps):
+        one_step()
+        if world > 1:
+            torch.cuda.synchronize()
+            b = sim.unpack_block_vector(vec_t.cpu().numpy())[0]
+        else:
+            sim.sync()
+            b = sim.get_block()[0]
+        upd_cls += np.array(b["bead_updates"], dtype=float)
+        kernel_ms += sim.last_block_ms()
+    ev1.record(lib_stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = sim.launch_count() - l0
+    clocks = sampler.stop()
+    t_ms = torch.tensor([dev_ms, wall * 1e3, kernel_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        # bead-updates counted in the all-reduced vector are already global
+        upd_total = float(upd_cls.sum())
+    else:
+        upd_total = float(upd_cls.sum())
+    dev_ms, wall_ms, kernel_ms = (float(x) for x in t_ms.cpu())
+    value = upd_total / (dev_ms * 1e-3)
+
+    # ---- e2e: the same K steps through the C ABI with HOST buffers (state up, block, results + state down)
+    barrier()
+    e2e_upd = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.set_state_all(hP.numpy(), hX.numpy(), hO.numpy(), hW.numpy())
+        one_step()
+        if world > 1:
+            torch.cuda.synchronize()
+            b = sim.unpack_block_vector(vec_t.cpu().numpy())[0]
+        else:
+            sim.sync()
+            b = sim.get_block()[0]
+        e2e_upd += float(sum(b["bead_updates"]))
+        Pn, xn, on, wn = sim.get_state_all()
+        hP.numpy()[...] = Pn
+        hX.numpy()[...] = xn
+        hO.numpy()[...] = on
+        hW.numpy()[...] = wn
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = e2e_upd / float(e2e_t.item())
+    state_bytes = hP.numel() * 8 + hX.numel() * 8 + 2 * n_chains * 4
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (the persistent sweep kernel)
+    fl = flops_per_bead_update(cfg["Np"])
+    if world > 1:
+        flops = sum(f * n for f, n in zip(fl, upd_cls)) / world      # this rank's share of the global count
+    else:
+        flops = sum(f * n for f, n in zip(fl, upd_cls))
+    peak = measure_fp64_peak(local)
+    achieved = flops / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(WORKLOAD, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic,
+                "note": "FP64 vector pipe (DFMA); peak measured live with pigs_measure_fp64_peak (MEASURED_PEAKS.json has "
+                        "no FP64 entry); achieved = algorithmic flops 2(N-1)c+40 per bead-update (c=28/46/37 by slice "
+                        "class) / CUDA-event time of the sweep kernel launches"}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "Np": cfg["Np"], "Nb": cfg["Nb"], "chains_per_gpu": n_chains,
+                   "mc_steps_per_step": nstep, "rng": "philox", "worm": "on (CWorm=0.5, Nobdm=10, swap)",
+                   "estimators": "mixed+thermodynamic energy, g(r), S(k), OBDM",
+                   "l2": f"inputs larger than L2: {state_bytes / 1e6:.0f} MB of paths per GPU stream from HBM",
+                   "parallelism": f"{world} x independent chain shards, one NCCL all-reduce of the block vector per step"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
+                "d2h_bytes_per_step": state_bytes + nvec * 8},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "wall_ms_per_step": wall_ms / args.steps,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(cfg)
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--mc-steps", type=int, default=MC_STEPS_PER_BLOCK, help="driver MC steps per bench step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                      # timing hygiene: at least 3 warm-up steps
+    from pathintegralgroundstate_b200.workloads import config
+    cfg = config(WORKLOAD)
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

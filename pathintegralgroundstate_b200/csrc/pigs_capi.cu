@@ -28,7 +28,7 @@ static int fail(int code, const std::string& m) { g_err = m; return code; }
 struct pigs_ctx {
     pigs_params hp;
     DevParams P;
-    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32, prefetch = 1;
+    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32, prefetch = 2;
     size_t smem = 0;
     int nvec = 0;
     bool tables_set = false;
@@ -157,7 +157,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     h->mt = p->rng_mode == PIGS_RNG_MT_REPLAY ? 1 : 0;
     {
         const char* e = getenv("PIGS_PREFETCH");      // tuning knob (default on)
-        if (e) h->prefetch = atoi(e) != 0;
+        if (e) h->prefetch = atoi(e);
     }
     DevParams& P = h->P;
     std::memset(&P, 0, sizeof P);

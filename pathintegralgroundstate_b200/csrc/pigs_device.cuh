@@ -593,6 +593,13 @@ __device__ __forceinline__ double bead_eval(const double* tV, const double* tW, 
     return 0.0;
 }
 
+// Bulk (TMA-engine) prefetch into L2 of whole time slices: one instruction per
+// slice.  With thousands of resident chains the paths live in HBM; ncu showed
+// the partner loop stalled on HBM latency that a one-iteration register
+// pipeline cannot cover, while L2 latency it can.
+__device__ __forceinline__ void prefetch_slice_L2(const double* slice_ptr) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(slice_ptr), "r"(3 * cP.NpS * 8) : "memory");
+}
 // L1 prefetch of the slices a move is going to read (other particles of the
 // displaced beads' time slices): issued at move start so the HBM/L2 latency
 // overlaps the proposal generation (ncu: 31% of stall samples sat on the first

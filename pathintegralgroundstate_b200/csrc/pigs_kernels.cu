@@ -6,12 +6,15 @@
 #error "define PIGS_INST_MT (0|1) and PIGS_INST_VAR (0..3)"
 #endif
 #ifndef PIGS_MAXT
-#define PIGS_MAXT 1024
+#define PIGS_MAXT 512
 #endif
 
 namespace pigs {
 
 // One CTA per SM (tables in shared memory) of up to PIGS_MAXT threads = G chain groups.
+// PIGS_MAXT = 512 gives the move engine 128 registers per thread: measured on
+// B200, 16 spill-free warps per SM beat 24 (80 regs) and 32 (64 regs, spilling
+// in the partner loop) for both the N=64 and the N=256 workloads.
 __global__ void __launch_bounds__(PIGS_MAXT, 1) PIGS_KNAME() { sweep_body<(PIGS_INST_MT != 0), PIGS_INST_VAR>(); }
 
 cudaError_t PIGS_LNAME(int what, const DevParams* P, const SweepArgs* A, int grid, int block, size_t smem,

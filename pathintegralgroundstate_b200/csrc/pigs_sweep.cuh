@@ -162,7 +162,7 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
     const int half = (flags & MV_HALF_MASK) >> 2;
     const int L = ie - ii;
     const int dim = cP.dim;
-    if (cA.prefetch) prefetch_slices(gs->path, (type == MV_TRANSLATE) ? ii : m0, ((type == MV_TRANSLATE) ? ie : m1) - ((type == MV_TRANSLATE) ? ii : m0) + 1, G.tid, G.size);
+    if (cA.prefetch == 1) prefetch_slices(gs->path, (type == MV_TRANSLATE) ? ii : m0, ((type == MV_TRANSLATE) ? ie : m1) - ((type == MV_TRANSLATE) ? ii : m0) + 1, G.tid, G.size);
     if (half) {
         if (G.tid < dim) pth(gs, G.tid, ip0, cP.Nb) = gs->xend[(half - 1) * 3 + G.tid];
         gsync();
@@ -210,6 +210,7 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
             if (gate) { b0 = iend; bs = 1; nb = 1; }
             else { b0 = ii + (delta_ib >> 1); bs = delta_ib; nb = 1 << (lev - 1); }
         } else { b0 = m0; bs = 1; nb = m1 - m0 + 1; }
+        if (cA.prefetch == 2 && G.tid < nb) prefetch_slice_L2(slice(gs, b0 + G.tid * bs));
         if (MT) {      // the reference's draw order (Appendix A of SURVEY.md)
             if (type == MV_BRIDGE) {
                 if (flags & MV_FREE_PREV) { rng_gauss_fill<MT>(gs, &ctr, dim, ie, 1, 1); rng_gauss_fill<MT>(gs, &ctr, dim, ii + 1, 1, L - 1); }

@@ -17,9 +17,12 @@ C2 = dict(dim=3, Np=64, density=0.365, trap=False, dt=5e-3, Nb=15, seed=1982, de
 # C3: liquid He-4 N=256, worm on                                   -- configs[2]
 C3 = dict(C2, Np=256, CWorm=0.5, Nobdm=10)
 # small worm configuration for fast replay tests
-CW = dict(C2, Np=16, Nb=8, Lstag=6, Nlev=2, CWorm=2.0, Nobdm=3, Nstag=2, Nk=8, Nbin=40)
+# CWorm chosen so that open and close are both accepted often (open ~ CWorm*rho*(2 pi Ls dt)^1.5)
+CW = dict(C2, Np=16, Nb=8, Lstag=6, Nlev=2, CWorm=5.0, Nobdm=3, Nstag=2, Nk=8, Nbin=40)
+# a large time step makes swap (exchange) moves acceptable: exercises Swap + permutation bookkeeping
+CWX = dict(CW, dt=0.04, Lstag=8, CWorm=3.0)
 # staging flavour
-CS = dict(CW, sampling="sta")
+CS = dict(CWX, sampling="sta")
 
 
 def oracle_cfg(cfg):

@@ -8,7 +8,7 @@ the same seeded inputs.  Tolerances (BASELINE.json north_star):
 import numpy as np
 import pytest
 
-from tests.common import C1, C2, C3, CW, CS, make_pair, synthetic_path, rel_err, oracle_cfg
+from tests.common import C1, C2, C3, CW, CWX, CS, make_pair, synthetic_path, rel_err, oracle_cfg
 from oracle.pigs_oracle import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -187,13 +187,13 @@ def test_diagonal_moves_replay(cfgname, tpc):
 
 @pytest.mark.parametrize("tpc", [32, 64])
 def test_worm_moves_replay(tpc):
-    cfg = CW
+    cfg = CWX
     rng = np.random.default_rng(9)
     o, g = make_pair(cfg, n_chains=1, rng="mt", threads_per_chain=tpc)
     iw = 5
     _sync_state(o, g, cfg, rng, chain=0, isopen=1, iworm=iw, seed=99)
     seq = []
-    for rep in range(6):
+    for rep in range(12):
         for gname, oname in HALF_MOVES:
             for half in (1, 2):
                 seq.append((gname, oname, iw, half))
@@ -210,15 +210,16 @@ def test_worm_moves_replay(tpc):
     mt_o, mti_o = o.get_mt()
     mt_g, mti_g = g.get_mt(0)
     assert mti_o == mti_g and np.array_equal(mt_o, mt_g)
+    assert n_swap > 0          # the exchange branch was taken
 
 
 def test_open_close_replay():
-    cfg = CW
+    cfg = CWX
     rng = np.random.default_rng(21)
     o, g = make_pair(cfg, n_chains=1, rng="mt")
     _sync_state(o, g, cfg, rng, chain=0, seed=4242)
     opened = closed = 0
-    for it in range(60):
+    for it in range(150):
         Po, xo, io, iw = o.get_state()
         if not io:
             ip = int(rng.integers(1, cfg["Np"] + 1))
@@ -256,6 +257,7 @@ def _replay_block(cfg, nchain, nstep, nblock, tables="reference", **kw):
         oc.set_state(P0[c], xe0[c], 0, 0)
         oc.sgrnd(1982 + c)
         oracles.append(oc)
+    totals = {k: 0 for k in INT_KEYS}
     for blk in range(nblock):
         g.run_block(nstep)
         tot = None
@@ -264,6 +266,7 @@ def _replay_block(cfg, nchain, nstep, nblock, tables="reference", **kw):
             bg, grg, Skg, nrg = g.get_block(chain=c)
             for k in INT_KEYS:
                 assert int(bg[k]) == int(b[k]), f"block {blk} chain {c}: {k} {bg[k]} != {b[k]}"
+                totals[k] += int(b[k])
             assert list(bg["bead_updates"]) == list(b["bead_updates"])
             for k in SUM_KEYS:
                 assert close(bg[k], b[k], 1e-9), f"block {blk} chain {c}: {k} {bg[k]} vs {b[k]}"
@@ -287,17 +290,19 @@ def _replay_block(cfg, nchain, nstep, nblock, tables="reference", **kw):
         bs, grs, Sks, nrs = g.get_block()
         got = np.array([bs[k] for k in SUM_KEYS] + [bs[k] for k in INT_KEYS])
         assert close(got, tot, 1e-9)
-    return oracles, g
+    return oracles, g, totals
 
 
 def test_run_block_replay_worm_bisection():
-    oracles, g = _replay_block(CW, nchain=3, nstep=12, nblock=2)
-    # the worm sector was actually visited
-    assert any(oc.get_perm()[2].sum() > 0 or oc.get_state()[2] for oc in oracles) or True
+    oracles, g, tot = _replay_block(CWX, nchain=3, nstep=15, nblock=3)
+    # the worm sector was actually visited, with accepted open / close / swap moves
+    assert tot["acc_open"] > 0 and tot["acc_close"] > 0 and tot["acc_swap"] > 0 and tot["try_stag_half"] > 0
+    assert sum(oc.get_perm()[2].sum() for oc in oracles) > 0           # Perm_histogram filled
 
 
 def test_run_block_replay_worm_staging():
-    _replay_block(CS, nchain=2, nstep=10, nblock=2, threads_per_chain=64)
+    _, _, tot = _replay_block(CS, nchain=2, nstep=10, nblock=2, threads_per_chain=64)
+    assert tot["acc_head"] > 0 and tot["acc_tail"] > 0 and tot["acc_bd"] > 0
 
 
 def test_run_block_replay_c2():
@@ -305,7 +310,7 @@ def test_run_block_replay_c2():
 
 
 def test_run_block_replay_c1_trap():
-    oracles, g = _replay_block(C1, nchain=2, nstep=6, nblock=1, tables="zero")
+    oracles, g, _ = _replay_block(C1, nchain=2, nstep=6, nblock=1, tables="zero")
     b, _, _, _ = g.get_block()
     # zero-variance mixed estimator: E = dim*N/2 every step
     assert abs(b["sumE"] / b["idiag_block"] - 12.0) < 1e-9
