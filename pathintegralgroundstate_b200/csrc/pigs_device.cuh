@@ -445,82 +445,69 @@ __device__ __forceinline__ PairGeom pair_geom(bool valid, double x0, double x1, 
 
 __device__ __forceinline__ int bead_kind(int ib) { return (ib == 0 || ib == 2 * cP.Nb) ? 2 : (ib & 1); }
 
-// interior even slice: returns the lane's share of PotNew-PotOld
-template <bool TRAP, bool VSM>
-__device__ __forceinline__ double pair_loop_even(const double* tV, const double* Rx, int ip0, int j0, int jstride,
-                                                 const double (&xo)[3], const double (&xn)[3]) {
-    const double* Ry = Rx + cP.NpS;
-    const double* Rz = Ry + cP.NpS;
-    double pot = 0.0;
-    // software pipeline: the next partner's coordinates are in flight while this one is evaluated
-    double nx = 0.0, ny = 0.0, nz = 0.0;
-    if (j0 < cP.Np) { nx = Rx[j0]; ny = Ry[j0]; nz = Rz[j0]; }
-PIGS_PRAGMA_UNROLL
-    for (int j = j0; j < cP.Np; j += jstride) {
-        const bool valid = (j != ip0);
-        const double rx = nx, ry = ny, rz = nz;
-        const int jn = j + jstride;
-        if (jn < cP.Np) { nx = Rx[jn]; ny = Ry[jn]; nz = Rz[jn]; }
-        PairGeom gn = pair_geom<0, TRAP, true>(valid, xn[0], xn[1], xn[2], rx, ry, rz);
-        PairGeom go = pair_geom<0, TRAP, false>(valid, xo[0], xo[1], xo[2], rx, ry, rz);
-        double vn = lk_val<VSM, 0, VSM>(gn.k), vo = lk_val<VSM, 0, VSM>(go.k);
-        pot += (gn.in_pot ? vn : 0.0) - (go.in_pot ? vo : 0.0);
-    }
-    return pot;
+// coherent global load of a path coordinate (the path is written by this group
+// during the kernel, so no .nc; an explicit ld.global avoids the generic-address
+// resolution of a plain pointer dereference)
+__device__ __forceinline__ double ldpath(const double* p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
 }
-// end slice: pot and psi
+struct Partner {
+    double x, y, z;
+};
+__device__ __forceinline__ Partner load_partner(const double* Rx, int j) {
+    Partner p;
+    p.x = ldpath(Rx + j); p.y = ldpath(Rx + cP.NpS + j); p.z = ldpath(Rx + 2 * cP.NpS + j);
+    return p;
+}
+
+// ONE partner loop for the three slice classes (kind is warp-uniform, so the
+// class-specific parts are skipped by uniform branches): the hot code of all
+// warps of a scheduler is then the same ~2.5 KB and stays in the L0 instruction
+// cache (three specialised loops were 6.6 KB; ncu showed 1.3 no_instruction
+// stall cycles per issue).
+// acc: pot, psi, fn[3], fo[3].  `first` = coordinates of partner j0, preloaded
+// by the caller (during the previous bead's reduction / the proposal).
 template <bool TRAP, bool VSM, bool WSM>
-__device__ __forceinline__ void pair_loop_end(const double* tV, const double* tW, const double* Rx, int ip0, int j0,
-                                              int jstride, const double (&xo)[3], const double (&xn)[3], double& pot,
-                                              double& psi) {
-    const double* Ry = Rx + cP.NpS;
-    const double* Rz = Ry + cP.NpS;
-    double nx = 0.0, ny = 0.0, nz = 0.0;
-    if (j0 < cP.Np) { nx = Rx[j0]; ny = Ry[j0]; nz = Rz[j0]; }
+__device__ __forceinline__ void pair_loop(int kind, const double* Rx, int ip0, int j0, int jstride, const double (&xo)[3],
+                                          const double (&xn)[3], Partner nxt, double& pot, double& psi, double (&fn)[3],
+                                          double (&fo)[3]) {
 PIGS_PRAGMA_UNROLL
     for (int j = j0; j < cP.Np; j += jstride) {
         const bool valid = (j != ip0);
-        const double rx = nx, ry = ny, rz = nz;
+        const Partner cur = nxt;
         const int jn = j + jstride;
-        if (jn < cP.Np) { nx = Rx[jn]; ny = Ry[jn]; nz = Rz[jn]; }
-        PairGeom gn = pair_geom<2, TRAP, true>(valid, xn[0], xn[1], xn[2], rx, ry, rz);
-        PairGeom go = pair_geom<2, TRAP, false>(valid, xo[0], xo[1], xo[2], rx, ry, rz);
-        double vn = lk_val<VSM, 0, VSM>(gn.k), vo = lk_val<VSM, 0, VSM>(go.k);
-        double wn = lk_val<WSM, 1, VSM>(gn.k), wo = lk_val<WSM, 1, VSM>(go.k);
-        pot += (gn.in_pot ? vn : 0.0) - (go.in_pot ? vo : 0.0);
-        psi += (gn.in_wf ? wn : 0.0) - (go.in_wf ? wo : 0.0);
-    }
-}
-// odd slice: pot and the moved particle's force at the new / old position (Q2)
-template <bool TRAP, bool VSM>
-__device__ __forceinline__ void pair_loop_odd(const double* tV, const double* Rx, int ip0, int j0, int jstride,
-                                              const double (&xo)[3], const double (&xn)[3], double& pot, double (&fn)[3],
-                                              double (&fo)[3]) {
-    const double* Ry = Rx + cP.NpS;
-    const double* Rz = Ry + cP.NpS;
-    double nx = 0.0, ny = 0.0, nz = 0.0;
-    if (j0 < cP.Np) { nx = Rx[j0]; ny = Ry[j0]; nz = Rz[j0]; }
-PIGS_PRAGMA_UNROLL
-    for (int j = j0; j < cP.Np; j += jstride) {
-        const bool valid = (j != ip0);
-        const double rx = nx, ry = ny, rz = nz;
-        const int jn = j + jstride;
-        if (jn < cP.Np) { nx = Rx[jn]; ny = Ry[jn]; nz = Rz[jn]; }
-        {
-            PairGeom g = pair_geom<1, TRAP, true>(valid, xn[0], xn[1], xn[2], rx, ry, rz);
-            double v, dv;
-            lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
-            pot += g.in_pot ? v : 0.0;
-            double s = g.in_pot ? dv * g.ir : 0.0;
-            fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
-        }
-        {
-            PairGeom g = pair_geom<1, TRAP, false>(valid, xo[0], xo[1], xo[2], rx, ry, rz);
-            double v, dv;
-            lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
-            pot -= g.in_pot ? v : 0.0;
-            double s = g.in_pot ? dv * g.ir : 0.0;
-            fo[0] += s * g.d0; fo[1] += s * g.d1; fo[2] += s * g.d2;
+        if (jn < cP.Np) nxt = load_partner(Rx, jn);       // software pipeline: next partner in flight
+        if (kind == 1) {
+            {
+                PairGeom g = pair_geom<1, TRAP, true>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z);
+                double v, dv;
+                lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
+                pot += g.in_pot ? v : 0.0;
+                double s = g.in_pot ? dv * g.ir : 0.0;
+                fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
+            }
+            {
+                PairGeom g = pair_geom<1, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z);
+                double v, dv;
+                lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
+                pot -= g.in_pot ? v : 0.0;
+                double s = g.in_pot ? dv * g.ir : 0.0;
+                fo[0] += s * g.d0; fo[1] += s * g.d1; fo[2] += s * g.d2;
+            }
+        } else {
+            // even and end slices share the geometry (in trap mode the end slice has no Jastrow cutoff)
+            PairGeom gn = (TRAP && kind == 2) ? pair_geom<2, TRAP, true>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z)
+                                              : pair_geom<0, TRAP, true>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z);
+            PairGeom go = (TRAP && kind == 2) ? pair_geom<2, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z)
+                                              : pair_geom<0, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z);
+            double vn = lk_val<VSM, 0, VSM>(gn.k), vo = lk_val<VSM, 0, VSM>(go.k);
+            pot += (gn.in_pot ? vn : 0.0) - (go.in_pot ? vo : 0.0);
+            if (kind == 2) {
+                double wn = lk_val<WSM, 1, VSM>(gn.k), wo = lk_val<WSM, 1, VSM>(go.k);
+                psi += (gn.in_wf ? wn : 0.0) - (go.in_wf ? wo : 0.0);
+            }
         }
     }
 }
@@ -541,11 +528,12 @@ __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
 //                   (UpdateAction, vpi_mod.f90:2491-2530), identical in every lane;
 //  part != nullptr: the warp's partial sums are stored to part[0..7] for a later
 //                   combination with other warps (returns 0).
-// The lane with add_self adds the one-body (trap) terms once.
+// The lane with add_self adds the one-body (trap) terms once.  `first` holds the
+// coordinates of partner j0 (preloaded by the caller; unused lanes pass anything).
 template <bool TRAP, bool VSM, bool WSM>
-__device__ __forceinline__ double bead_eval(const double* tV, const double* tW, const double* Rx, int ip0, int ib, int j0,
-                                            int jstride, bool add_self, const double (&xo)[3], const double (&xn)[3],
-                                            int lane, double* part) {
+__device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, int j0, int jstride, bool add_self,
+                                            const double (&xo)[3], const double (&xn)[3], int lane, double* part,
+                                            const Partner& first) {
     const int kind = bead_kind(ib);
     const double dt = cP.dt;
     double pot = 0.0, psi = 0.0, fn[3] = {0.0, 0.0, 0.0}, fo[3] = {0.0, 0.0, 0.0};
@@ -560,15 +548,14 @@ __device__ __forceinline__ double bead_eval(const double* tV, const double* tW, 
             }
         }
     }
+    pair_loop<TRAP, VSM, WSM>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
     if (kind == 0) {
-        pot += pair_loop_even<TRAP, VSM>(tV, Rx, ip0, j0, jstride, xo, xn);
         double v = warp_sum(pot);
         if (!part) return (2.0 * dt / 3.0) * v;
         if (lane < 8) part[lane] = (lane == 0) ? v : 0.0;
         return 0.0;
     }
     if (kind == 2) {
-        pair_loop_end<TRAP, VSM, WSM>(tV, tW, Rx, ip0, j0, jstride, xo, xn, pot, psi);
         double v = warp_sum2(pot, psi, lane);          // lanes 0..15: pot, lanes 16..31: psi
         if (!part) {
             double t = (lane & 16) ? -v : (dt / 3.0) * v;
@@ -579,7 +566,6 @@ __device__ __forceinline__ double bead_eval(const double* tV, const double* tW, 
         if (lane >= 2 && lane < 8) part[lane] = 0.0;
         return 0.0;
     }
-    pair_loop_odd<TRAP, VSM>(tV, Rx, ip0, j0, jstride, xo, xn, pot, fn, fo);
     const double a[8] = {pot, 0.0, fn[0], fn[1], fn[2], fo[0], fo[1], fo[2]};
     double v = warp_sum8(a, lane);                      // quad q holds value q
     const int q = lane >> 2;

@@ -75,11 +75,17 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         split = nw / nb;
         if (split > nch) split = nch;
     }
-    const double* tV = gs->tabV;
-    const double* tW = gs->tabW;
     double* part = part_of(gs);
     const int ntask = nb * split;
     double Sw = 0.0;
+    // the first partner of a task is loaded one task ahead, so its HBM/L2 latency hides behind the previous
+    // task's reduction (or, for the first task, behind the coordinate reads below)
+    Partner first;
+    first.x = first.y = first.z = 0.0;
+    if (G.warp < ntask) {
+        int m = (split > 1) ? G.warp / split : G.warp, s = (split > 1) ? G.warp - m * split : 0;
+        if (s * 32 + G.lane < cP.Np) first = load_partner(slice(gs, b0 + m * bstride), s * 32 + G.lane);
+    }
     for (int task = G.warp; task < ntask; task += nw) {
         int m = task, s = 0;
         if (split > 1) { m = task / split; s = task - m * split; }
@@ -87,9 +93,15 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         double xo[3], xn[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) { xo[k] = so(gs, k, ib); xn[k] = sn(gs, k, ib); }
-        double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM>(tV, tW, slice(gs, ib), ip0, ib, s * 32 + G.lane, 32 * split,
+        const Partner cur = first;
+        const int tn = task + nw;
+        if (tn < ntask) {
+            int mn = (split > 1) ? tn / split : tn, sn_ = (split > 1) ? tn - mn * split : 0;
+            if (sn_ * 32 + G.lane < cP.Np) first = load_partner(slice(gs, b0 + mn * bstride), sn_ * 32 + G.lane);
+        }
+        double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM>(slice(gs, ib), ip0, ib, s * 32 + G.lane, 32 * split,
                                                            (s == 0) && (G.lane == 0), xo, xn, G.lane,
-                                                           (split == 1) ? nullptr : part + task * 8);
+                                                           (split == 1) ? nullptr : part + task * 8, cur);
         if (split == 1) {
             double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
             Sw += w * t;

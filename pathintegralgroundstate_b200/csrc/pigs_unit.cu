@@ -91,8 +91,11 @@ __global__ void __launch_bounds__(128) k_update_action(int n, const double* Rsoa
         double xo[3] = {0, 0, 0}, xn[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 3; ++k) if (k < cP.dim) { xo[k] = xold[e * cP.dim + k]; xn[k] = xnew[e * cP.dim + k]; }
-        double t = bead_eval<TRAP, false, false>(cP.vtab, cP.logwf, Rsoa + (size_t)e * 3 * cP.NpS, ip[e] - 1, ib[e], lane, 32,
-                                                 lane == 0, xo, xn, lane, nullptr);
+        const double* Rx = Rsoa + (size_t)e * 3 * cP.NpS;
+        Partner first;
+        first.x = first.y = first.z = 0.0;
+        if (lane < cP.Np) first = load_partner(Rx, lane);
+        double t = bead_eval<TRAP, false, false>(Rx, ip[e] - 1, ib[e], lane, 32, lane == 0, xo, xn, lane, nullptr, first);
         if (lane == 0) dS[e] = t;
     }
 }
