@@ -284,7 +284,11 @@ def run_ours(args, cfg):
     e2e_val = e2e_upd / float(e2e_t.item())
     state_bytes = hP.numel() * 8 + hX.numel() * 8 + 2 * n_chains * 4
 
+    if world > 1:
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel (the persistent sweep kernel)
     fl = flops_per_bead_update(cfg["Np"])
@@ -325,6 +329,8 @@ def run_ours(args, cfg):
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(cfg)
     print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

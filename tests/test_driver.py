@@ -1,0 +1,106 @@
+"""The driver layer (vpi.f90 outer loop on top of the C ABI): Fortran edit
+descriptors, checkpoint/rand_state formats, and the whole driver run over the
+CPU oracle (CPU test) and over libpigs_cuda (GPU test) with the files compared."""
+import os
+
+import numpy as np
+import pytest
+
+from pathintegralgroundstate_b200.driver import (fortran_g, fortran_e, fortran_f, g_line, var, write_checkpoint,
+                                                 read_checkpoint, append_rand_state, read_rand_state, VpiDriver)
+from tests.common import C1, CWX, CW
+from tests.oracle_backend import OracleBackend
+
+
+def test_fortran_g_editing():
+    # Gw.dEe: F editing + e+2 trailing blanks inside [0.1, 10^d), E editing outside (F2003 10.6.4.1.2)
+    assert fortran_g(1.0) == "    1.000000000     "
+    assert fortran_g(0.5) == "   0.5000000000     "
+    assert fortran_g(123.456) == "    123.4560000     "
+    assert fortran_g(-3.4187286) == "   -3.418728600     "
+    assert fortran_g(0.0) == "    0.000000000     "
+    assert fortran_g(1.0e-5) == "   0.1000000000E-004"
+    assert fortran_g(-2.5e12) == "  -0.2500000000E+013"
+    assert fortran_g(9999999999.4) == "    9999999999.     "
+    assert fortran_g(0.09999999999) == "   0.9999999999E-001"
+    assert fortran_g(float("nan")).strip() == "NaN"
+    assert len(g_line([1.0, 2.0, 3.0])) == 61
+    assert fortran_e(0.1, 20, 10, 3) == "   0.1000000000E+000"
+    assert fortran_f(12.0, 7, 2) == "  12.00"
+    assert fortran_g(5.25, 16, 8, 2) == "   5.2500000    "
+    assert var(4, 2.0, 5.0) == 0.5
+
+
+def test_checkpoint_and_rand_state_formats(tmp_path):
+    rng = np.random.default_rng(0)
+    P = rng.normal(size=(5, 3, 3))
+    xe = rng.normal(size=(2, 3))
+    f = tmp_path / "checkpoint.dat"
+    write_checkpoint(f, False, P, xe, True, 2)
+    trap, isopen, iworm, P2, xe2 = read_checkpoint(f, 3, 3, 2)
+    assert (trap, isopen, iworm) == (False, True, 2)
+    assert np.array_equal(P, P2) and np.array_equal(xe, xe2)          # 17 significant digits survive
+    lines = open(f).read().splitlines()
+    assert lines[0].strip() == ".False." and lines[1].strip() == ".True." and len(lines) == 3 + 15 + 2 + 2
+    r = tmp_path / "rand_state"
+    mt = rng.integers(0, 2 ** 32, 624, dtype=np.uint64).astype(np.uint32)
+    append_rand_state(r, mt, 17)
+    append_rand_state(r, mt[::-1].copy(), 99)          # the file only grows ...
+    mt2, mti2 = read_rand_state(r)
+    assert mti2 == 17 and np.array_equal(mt2, mt)      # ... and resume reads the OLDEST record (Q10)
+    assert os.path.getsize(r) == 2 * (12 + 4 + 2496 + 4)
+
+
+def test_driver_over_oracle_trap_zero_variance(tmp_path):
+    """C1 (BASELINE configs[0]): non-interacting bosons in a trap -> the mixed estimator is exactly dim/2 per particle"""
+    cfg = dict(C1, Nblock=2, Nstep=4, resume=False)
+    d = VpiDriver(cfg, OracleBackend(cfg), workdir=str(tmp_path), potential="zero", quiet=True)
+    res = d.run()
+    assert res["diag_bl"] == 2 and abs(res["E"] - 1.5) < 1e-12
+    rows = [ln.split() for ln in open(tmp_path / "e_vpi.out")]
+    assert len(rows) == 2 and float(rows[0][0]) == 1.0 and abs(float(rows[1][1]) - 1.5) < 1e-9
+    assert os.path.exists(tmp_path / "checkpoint.dat") and os.path.exists(tmp_path / "rand_state")
+    assert not os.path.exists(tmp_path / "gr_vpi.out")            # structural estimators are PBC-only (vpi.f90:466)
+    # resume: a second driver picks the state and the (oldest) random state up
+    cfg2 = dict(cfg, resume=True, Nblock=1)
+    d2 = VpiDriver(cfg2, OracleBackend(cfg2), workdir=str(tmp_path), potential="zero", quiet=True)
+    assert abs(d2.run()["E"] - 1.5) < 1e-12
+
+
+def test_driver_over_oracle_writes_all_files(tmp_path):
+    cfg = dict(CWX, Nblock=3, Nstep=6)
+    res = VpiDriver(cfg, OracleBackend(cfg), workdir=str(tmp_path), quiet=True).run()
+    for f in ("e_vpi.out", "et_vpi.out", "gr_vpi.out", "sk_vpi.out", "jastrow.out", "potential.out", "fort.99",
+              "checkpoint.dat", "rand_state"):
+        assert os.path.getsize(tmp_path / f) > 0, f
+    gr = np.loadtxt(tmp_path / "gr_vpi.out")
+    assert gr.shape == (cfg["Nbin"], 3) and np.all(gr[:5, 1] == 0) and gr[-10:, 1].mean() > 0.3
+    sk = np.loadtxt(tmp_path / "sk_vpi.out")
+    assert sk.shape == (cfg["Nk"], 9)
+    pot = np.loadtxt(tmp_path / "potential.out", max_rows=5000)
+    assert pot.shape[1] == 2 and np.isnan(pot[0, 1])
+    assert len(open(tmp_path / "fort.99").read().split()) == 2 * cfg["Np"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfgname", ["CWX", "C1"])
+def test_driver_gpu_replay_matches_driver_over_oracle(tmp_path, cfgname):
+    from pathintegralgroundstate_b200 import PigsCuda
+    cfg = dict(dict(CWX=CWX, C1=C1)[cfgname], Nblock=3, Nstep=8)
+    pot = "zero" if cfgname == "C1" else "hfdb"
+    a, b = tmp_path / "oracle", tmp_path / "gpu"
+    VpiDriver(cfg, OracleBackend(cfg), workdir=str(a), potential=pot, quiet=True).run()
+    sim = PigsCuda(cfg, n_chains=1, rng="mt", seed=cfg["seed"])
+    VpiDriver(cfg, sim, workdir=str(b), potential=pot, quiet=True).run()
+    files = ["e_vpi.out", "et_vpi.out", "fort.99", "checkpoint.dat"]
+    if cfgname != "C1":
+        files += ["gr_vpi.out", "sk_vpi.out"]
+    for f in files:
+        x = np.array([float(t) for t in open(a / f).read().replace(".True.", "1").replace(".False.", "0").split()])
+        y = np.array([float(t) for t in open(b / f).read().replace(".True.", "1").replace(".False.", "0").split()])
+        assert x.shape == y.shape, f
+        ok = np.isclose(x, y, rtol=2e-7, atol=1e-9) | (np.isnan(x) & np.isnan(y))
+        assert ok.all(), (f, x[~ok][:4], y[~ok][:4])
+    # integer files are identical byte for byte; the random state record too
+    assert open(a / "fort.99").read() == open(b / "fort.99").read()
+    assert open(a / "rand_state", "rb").read() == open(b / "rand_state", "rb").read()
