@@ -86,6 +86,7 @@ static int plan(pigs_ctx* h) {
     if (T != 32 && T != 64 && T != 128 && T != 256 && T != 512) return fail(PIGS_E_ARG, "threads_per_chain must be 0,32,64,128,256,512");
     const size_t gbytes = (grp_smem_bytes(h->P.S, h->P.Np, T / 32) + 15) & ~(size_t)15;
     const size_t tabbytes = (size_t)(p.Nmax + 2) * sizeof(double);
+    const size_t pairbytes = (size_t)(p.Nmax + 1) * 2 * sizeof(double);      // table_mode 1: {F(i),F(i+1)} pairs
     int maxt = 1024;
     CK(sweep_max_threads(h->mt, p.trap ? 3 : 0, &maxt));
     if (T > maxt) return fail(PIGS_E_ARG, "threads_per_chain exceeds the kernel's launch bound");
@@ -100,14 +101,17 @@ static int plan(pigs_ctx* h) {
         if (tm < 0) {
             // both tables in shared memory when at least min(Gneed,4) groups still fit beside them
             int gmin = Gneed < 4 ? Gneed : 4;
-            if (2 * tabbytes + gmin * gbytes <= smem_max) tm = 2;
-            else if (tabbytes + gmin * gbytes <= smem_max) tm = 1;
+            int gfull = Gneed < Gmax ? Gneed : Gmax;
+            // measured on B200 (C2/C3): both plain tables in smem > V pair table in smem > tables via L1/L2
+            if (2 * tabbytes + (size_t)gfull * gbytes <= smem_max) tm = 2;
+            else if (pairbytes + (size_t)gfull * gbytes <= smem_max) tm = 1;
+            else if (2 * tabbytes + (size_t)gmin * gbytes <= smem_max) tm = 2;
             else tm = 0;
         }
         if (tm < 0 || tm > 2) return fail(PIGS_E_ARG, "table_mode must be -1,0,1,2");
         var = tm;
     }
-    const size_t fixed = (var == 1 ? tabbytes : (var == 2 ? 2 * tabbytes : 0));
+    const size_t fixed = (var == 1 ? pairbytes : (var == 2 ? 2 * tabbytes : 0));
     if (fixed + gbytes > smem_max) return fail(PIGS_E_ARG, "configuration does not fit in shared memory; lower table_mode");
     int G = (int)((smem_max - fixed) / gbytes);
     if (G > Gmax) G = Gmax;

@@ -142,12 +142,13 @@ __device__ __forceinline__ double& pth(GS* gs, int k, int ip0, int ib) { return 
 
 // ------------------------------------------------------------------ tables
 // VAR 0: both tables through the read-only L1/L2 path; 1: VTable in shared
-// memory, LogWF global; 2: both in shared memory; 3: trap (tables global).
+// memory as a PAIR table {F(i),F(i+1)} read with one LDS.128 per interpolant,
+// LogWF global; 2: both plain in shared memory; 3: trap (tables global).
 template <int VAR> struct VarTraits;
-template <> struct VarTraits<0> { static constexpr bool TRAP = false, VSM = false, WSM = false; };
-template <> struct VarTraits<1> { static constexpr bool TRAP = false, VSM = true,  WSM = false; };
-template <> struct VarTraits<2> { static constexpr bool TRAP = false, VSM = true,  WSM = true;  };
-template <> struct VarTraits<3> { static constexpr bool TRAP = true,  VSM = false, WSM = false; };
+template <> struct VarTraits<0> { static constexpr bool TRAP = false, VSM = false, WSM = false, VPAIR = false; };
+template <> struct VarTraits<1> { static constexpr bool TRAP = false, VSM = true,  WSM = false, VPAIR = true;  };
+template <> struct VarTraits<2> { static constexpr bool TRAP = false, VSM = true,  WSM = true,  VPAIR = false; };
+template <> struct VarTraits<3> { static constexpr bool TRAP = true,  VSM = false, WSM = false, VPAIR = false; };
 
 // Table reads with the address space known at compile time: the staged copies
 // sit at the start of dynamic shared memory (VTable first, then LogWF), so the
@@ -194,6 +195,25 @@ __device__ __forceinline__ Lk lk_prep(double r) {
     k.a1 = fma(-tf, cP.dr, r);
     k.a2 = cP.dr - k.a1;
     return k;
+}
+// VTable staged as pairs: entry i holds {F(i), F(i+1)} (16-byte aligned), so a linear
+// interpolant is ONE shared-memory request instead of two (ncu: 2 bank-conflict
+// cycles per LDS.64 on the random table indices of a warp).
+__device__ __forceinline__ double2 tabpair(int i) {
+    extern __shared__ __align__(16) double pigs_smem_base[];
+    return reinterpret_cast<const double2*>(pigs_smem_base)[i];
+}
+__device__ __forceinline__ double lk_val_pair(const Lk& k) {
+    double2 t = tabpair(k.i0);
+    return (k.a1 * t.y + k.a2 * t.x) * cP.inv_dr;
+}
+__device__ __forceinline__ void lk_val_d1_pair(const Lk& k, double& v, double& d1) {
+    double2 lo = tabpair(k.i0 - 1), hi = tabpair(k.i0 + 1);      // {fm,f0}, {f1,f2}
+    double Fc = k.a1 * hi.x + k.a2 * lo.y;
+    double Fb = k.a1 * lo.y + k.a2 * lo.x;
+    double Fa = k.a1 * hi.y + k.a2 * hi.x;
+    v = Fc * cP.inv_dr;
+    d1 = (Fa - Fb) * (0.5 * cP.inv_dr * cP.inv_dr);
 }
 template <bool SM, int WHICH, bool VF>
 __device__ __forceinline__ double lk_val(const Lk& k) {   // opt 0
@@ -470,14 +490,14 @@ __device__ __forceinline__ Partner load_partner(const double* Rx, int j) {
 // acc: pot, psi, fn[3], fo[3].  `first` = coordinates of partner j0, preloaded
 // by the caller (during the previous bead's reduction / the proposal).
 // both positions of the displaced bead against ONE partner
-template <bool TRAP, bool VSM, bool WSM>
+template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
 __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& cur, const double (&xo)[3],
                                           const double (&xn)[3], double& pot, double& psi, double (&fn)[3], double (&fo)[3]) {
     if (kind == 1) {
         {
             PairGeom g = pair_geom<1, TRAP, true>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z);
             double v, dv;
-            lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
+            if (VPAIR) lk_val_d1_pair(g.k, v, dv); else lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
             pot += g.in_pot ? v : 0.0;
             double s = g.in_pot ? dv * g.ir : 0.0;
             fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
@@ -485,7 +505,7 @@ __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& c
         {
             PairGeom g = pair_geom<1, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z);
             double v, dv;
-            lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
+            if (VPAIR) lk_val_d1_pair(g.k, v, dv); else lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
             pot -= g.in_pot ? v : 0.0;
             double s = g.in_pot ? dv * g.ir : 0.0;
             fo[0] += s * g.d0; fo[1] += s * g.d1; fo[2] += s * g.d2;
@@ -496,10 +516,11 @@ __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& c
                                           : pair_geom<0, TRAP, true>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z);
         PairGeom go = (TRAP && kind == 2) ? pair_geom<2, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z)
                                           : pair_geom<0, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z);
-        double vn = lk_val<VSM, 0, VSM>(gn.k), vo = lk_val<VSM, 0, VSM>(go.k);
+        double vn = VPAIR ? lk_val_pair(gn.k) : lk_val<VSM, 0, VSM>(gn.k);
+        double vo = VPAIR ? lk_val_pair(go.k) : lk_val<VSM, 0, VSM>(go.k);
         pot += (gn.in_pot ? vn : 0.0) - (go.in_pot ? vo : 0.0);
         if (kind == 2) {
-            double wn = lk_val<WSM, 1, VSM>(gn.k), wo = lk_val<WSM, 1, VSM>(go.k);
+            double wn = lk_val<WSM, 1, VSM && !VPAIR>(gn.k), wo = lk_val<WSM, 1, VSM && !VPAIR>(go.k);
             psi += (gn.in_wf ? wn : 0.0) - (go.in_wf ? wo : 0.0);
         }
     }
@@ -516,7 +537,7 @@ __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& c
 // B200: a two-deep pipeline, an A/B ping-pong body and a 2x unrolled body were
 // all 5-25% slower -- larger loop bodies lose more than the extra latency
 // tolerance gains.)
-template <bool TRAP, bool VSM, bool WSM>
+template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
 __device__ __forceinline__ void pair_loop(int kind, const double* Rx, int ip0, int j0, int jstride, const double (&xo)[3],
                                           const double (&xn)[3], Partner nxt, double& pot, double& psi, double (&fn)[3],
                                           double (&fo)[3]) {
@@ -525,7 +546,7 @@ PIGS_PRAGMA_UNROLL
         const Partner cur = nxt;
         const int jn = j + jstride;
         if (jn < cP.Np) nxt = load_partner(Rx, jn);
-        pair_body<TRAP, VSM, WSM>(kind, j != ip0, cur, xo, xn, pot, psi, fn, fo);
+        pair_body<TRAP, VSM, WSM, VPAIR>(kind, j != ip0, cur, xo, xn, pot, psi, fn, fo);
     }
 }
 
@@ -547,7 +568,7 @@ __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
 //                   combination with other warps (returns 0).
 // The lane with add_self adds the one-body (trap) terms once.  `first` holds the
 // coordinates of partner j0 (preloaded by the caller; unused lanes pass anything).
-template <bool TRAP, bool VSM, bool WSM>
+template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
 __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, int j0, int jstride, bool add_self,
                                             const double (&xo)[3], const double (&xn)[3], int lane, double* part,
                                             const Partner& first) {
@@ -565,7 +586,7 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
             }
         }
     }
-    pair_loop<TRAP, VSM, WSM>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
+    pair_loop<TRAP, VSM, WSM, VPAIR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
     if (kind == 0) {
         double v = warp_sum(pot);
         if (!part) return (2.0 * dt / 3.0) * v;

@@ -39,6 +39,7 @@ typedef unsigned long long ull;
 #define PIGS_TRAP (VarTraits<VAR>::TRAP)
 #define PIGS_VSM (VarTraits<VAR>::VSM)
 #define PIGS_WSM (VarTraits<VAR>::WSM)
+#define PIGS_VPAIR (VarTraits<VAR>::VPAIR)
 
 template <int VAR> __device__ __forceinline__ double bc_wrap(int k, double x) {      // BoundaryConditions unless trap
     return PIGS_TRAP ? x : mimg(x, cP.L[k], cP.Lh[k]);
@@ -99,7 +100,7 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
             int mn = (split > 1) ? tn / split : tn, sn_ = (split > 1) ? tn - mn * split : 0;
             if (sn_ * 32 + G.lane < cP.Np) first = load_partner(slice(gs, b0 + mn * bstride), sn_ * 32 + G.lane);
         }
-        double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM>(slice(gs, ib), ip0, ib, s * 32 + G.lane, 32 * split,
+        double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM, PIGS_VPAIR>(slice(gs, ib), ip0, ib, s * 32 + G.lane, 32 * split,
                                                            (s == 0) && (G.lane == 0), xo, xn, G.lane,
                                                            (split == 1) ? nullptr : part + task * 8, cur);
         if (split == 1) {
@@ -602,7 +603,7 @@ static __device__ __noinline__ void LocalEnergy(GS* gs, const double* Rx, double
                 F[0] += __ddiv_rn(__dmul_rn(dudr, d0), r);
                 F[1] += __ddiv_rn(__dmul_rn(dudr, d1), r);
                 F[2] += __ddiv_rn(__dmul_rn(dudr, d2), r);
-                pot += lk_exact_val<PIGS_VSM>(tV, r);
+                pot += PIGS_VPAIR ? lk_exact_val<false>(cP.vtab, r) : lk_exact_val<PIGS_VSM>(tV, r);
             }
         }
         s[0] += F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
@@ -658,12 +659,12 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
                 if (PIGS_TRAP) k.i0 = min(k.i0, cP.Nmax - 1);
                 if (odd) {
                     double v, dv;
-                    lk_val_d1<PIGS_VSM, 0, PIGS_VSM>(k, v, dv);
+                    if (PIGS_VPAIR) lk_val_d1_pair(k, v, dv); else lk_val_d1<PIGS_VSM, 0, PIGS_VSM>(k, v, dv);
                     pot += v;
                     double q = dv * ir;
                     F[0] += q * d0; F[1] += q * d1; F[2] += q * d2;
                 } else {
-                    pot += lk_val<PIGS_VSM, 0, PIGS_VSM>(k);
+                    pot += PIGS_VPAIR ? lk_val_pair(k) : lk_val<PIGS_VSM, 0, PIGS_VSM>(k);
                 }
             }
         }
@@ -880,7 +881,11 @@ PIGS_T __device__ __forceinline__ void sweep_body() {
     double* sp = smem;
     const double* tV = cP.vtab;
     const double* tW = cP.logwf;
-    if (VT::VSM) {
+    if (VT::VPAIR) {
+        // pair table: entry i = {F(i), F(i+1)}, i = 0..Nmax  (2*(Nmax+1) doubles, 16-byte aligned)
+        for (int i = threadIdx.x; i < ntab - 1; i += blockDim.x) { sp[2 * i] = cP.vtab[i]; sp[2 * i + 1] = cP.vtab[i + 1]; }
+        tV = cP.vtab; sp += 2 * (ntab - 1);
+    } else if (VT::VSM) {
         for (int i = threadIdx.x; i < ntab; i += blockDim.x) sp[i] = cP.vtab[i];
         tV = sp; sp += ntab;
     }

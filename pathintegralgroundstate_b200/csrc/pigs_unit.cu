@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) k_update_action(int n, const double* Rsoa
         Partner first;
         first.x = first.y = first.z = 0.0;
         if (lane < cP.Np) first = load_partner(Rx, lane);
-        double t = bead_eval<TRAP, false, false>(Rx, ip[e] - 1, ib[e], lane, 32, lane == 0, xo, xn, lane, nullptr, first);
+        double t = bead_eval<TRAP, false, false, false>(Rx, ip[e] - 1, ib[e], lane, 32, lane == 0, xo, xn, lane, nullptr, first);
         if (lane == 0) dS[e] = t;
     }
 }
