@@ -27,17 +27,20 @@ CS = dict(CWX, sampling="sta")
 
 def oracle_cfg(cfg):
     c = dict(cfg)
+    if c.get("crystal") and "Lbox" in c:
+        c["Lbox_crystal"] = list(c["Lbox"])
     for k in ("trap", "swapping", "wf_table", "v_table", "crystal"):
         if k in c:
             c[k] = int(bool(c[k]))
     return c
 
 
-def lattice(Np, L, jitter, rng):
+def lattice(Np, L, jitter, rng, dim=3):
     """simple-cubic lattice with >= Np sites centred in [-L/2,L/2), first Np sites, + uniform jitter"""
-    n = int(np.ceil(Np ** (1.0 / 3.0) - 1e-9))
+    n = int(np.ceil(Np ** (1.0 / dim) - 1e-9))
     g = (np.arange(n) + 0.5) * (L / n) - L / 2
-    R = np.array([[x, y, z] for x in g for y in g for z in g])[:Np]
+    grids = np.meshgrid(*([g] * dim), indexing="ij")
+    R = np.stack([x.ravel() for x in grids], axis=1)[:Np]
     return R + rng.uniform(-jitter, jitter, size=R.shape)
 
 
@@ -45,13 +48,18 @@ def synthetic_path(cfg, rng, spread=0.08, jitter=0.05):
     """a He-4-like configuration: lattice + per-particle jitter, beads scattered around it and wrapped"""
     o = Oracle(oracle_cfg(cfg))
     S = 2 * cfg["Nb"] + 1
+    dim = cfg["dim"]
     if cfg.get("trap"):
-        R0 = rng.uniform(-1.0, 1.0, size=(cfg["Np"], cfg["dim"]))
-        P = R0[None] + rng.normal(0, spread, size=(S, cfg["Np"], cfg["dim"]))
+        R0 = rng.uniform(-1.0, 1.0, size=(cfg["Np"], dim))
+        P = R0[None] + rng.normal(0, spread, size=(S, cfg["Np"], dim))
         return P
-    L = o.Lbox[0]
-    R0 = lattice(cfg["Np"], L, jitter, rng)
-    P = R0[None] + rng.normal(0, spread, size=(S, cfg["Np"], cfg["dim"]))
+    L = np.asarray(o.Lbox[:dim])
+    if cfg.get("crystal"):
+        from pathintegralgroundstate_b200.workloads import hcp_lattice
+        R0 = hcp_lattice(density=cfg["density"])[0][:cfg["Np"]] + rng.uniform(-jitter, jitter, size=(cfg["Np"], 3))
+    else:
+        R0 = lattice(cfg["Np"], L[0], jitter, rng, dim)
+    P = R0[None] + rng.normal(0, spread, size=(S, cfg["Np"], dim))
     P = (P + L / 2) % L - L / 2
     return P
 

@@ -251,6 +251,7 @@ def _replay_block(cfg, nchain, nstep, nblock, tables="reference", **kw):
     P0 = np.stack([synthetic_path(cfg, rng, spread=0.03) for _ in range(nchain)])
     xe0 = np.stack([np.stack([P0[c, cfg["Nb"], -1]] * 2) for c in range(nchain)])
     g.set_state_all(P0, xe0)
+    assert P0.shape[-1] == cfg["dim"]
     for c in range(nchain):
         oc = Oracle(oracle_cfg(cfg))
         oc.set_tables(*o.get_tables())
@@ -389,3 +390,56 @@ def test_full_size_properties_c3():
     assert gr.sum() <= b["ngr"] * cfg["Np"] * (cfg["Np"] - 1)
     assert gr.sum() > 0.4 * b["ngr"] * cfg["Np"] * (cfg["Np"] - 1) or b["ngr"] == 0
     assert sum(b["bead_updates"]) > 0
+
+
+# ------------------------------------------------------------------ more shapes of the same path
+def test_run_block_replay_hcp_crystal_c4():
+    """BASELINE configs[3] geometry: orthorhombic (non-cubic) box from config_ini.in, N=180, worm on"""
+    from pathintegralgroundstate_b200.workloads import config
+    cfg = dict(config("C4"), CWorm=8.0, Nstag=1)
+    cfg.pop("tables")
+    cfg["Lbox_crystal"] = cfg["Lbox"]
+    _replay_block(cfg, nchain=1, nstep=1, nblock=1)
+
+
+def test_run_block_replay_two_dimensions():
+    cfg = dict(CW, dim=2, Np=16, density=0.3, Nk=6)
+    _replay_block(cfg, nchain=2, nstep=8, nblock=1)
+
+
+@pytest.mark.parametrize("tpc", [256, 512])
+def test_wide_chain_groups(tpc):
+    """few chains -> many warps per chain: partners of one bead are split over warps"""
+    _replay_block(dict(C2, Nstag=1), nchain=1, nstep=1, nblock=1, threads_per_chain=tpc)
+
+
+def test_chain_count_not_a_multiple_of_the_group_count():
+    oracles, g, _ = _replay_block(CW, nchain=37, nstep=3, nblock=1, threads_per_chain=32)
+    assert g.n_chains == 37
+
+
+def test_many_chains_block_vector_is_the_sum_of_chains():
+    """size-independent property at throughput scale (configs[4] shape: thousands of N=64 chains)"""
+    cfg = dict(C2, Nstag=1)
+    rng = np.random.default_rng(0)
+    n = 1500
+    _, g = make_pair(cfg, n_chains=n, rng="philox", seed=11)
+    P0 = synthetic_path(cfg, rng, spread=0.03)
+    xe0 = np.stack([P0[cfg["Nb"], -1]] * 2)
+    g.set_state_all(np.broadcast_to(P0, (n,) + P0.shape).copy(), np.broadcast_to(xe0, (n, 2, 3)).copy())
+    g.run_block(2)
+    tot, gr, Sk, nr = g.get_block()
+    per = [g.get_block(chain=c) for c in range(0, n, 97)]
+    assert tot["idiag_block"] + tot["n_open_chains"] * 0 <= 2 * n and tot["ngr"] == tot["idiag_block"]
+    assert sum(tot["bead_updates"]) > 0 and tot["try_stag"] == 2 * n * cfg["Np"] * cfg["Nstag"]
+    # chains started from the same point with different Philox streams must decorrelate
+    e = np.array([p[0]["sumE"] for p in per])
+    assert np.unique(np.round(e, 6)).size > len(per) // 2
+    # g(r) counts: every diagonal step contributes at most N(N-1) counts
+    assert gr.sum() <= tot["ngr"] * cfg["Np"] * (cfg["Np"] - 1)
+    # the same seed gives the same result (determinism of the parallel reduction)
+    _, g2 = make_pair(cfg, n_chains=n, rng="philox", seed=11)
+    g2.set_state_all(np.broadcast_to(P0, (n,) + P0.shape).copy(), np.broadcast_to(xe0, (n, 2, 3)).copy())
+    g2.run_block(2)
+    tot2, gr2, _, _ = g2.get_block()
+    assert tot2 == tot and np.array_equal(gr, gr2)
