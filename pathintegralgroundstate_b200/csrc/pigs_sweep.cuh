@@ -598,12 +598,13 @@ static __device__ __noinline__ void LocalEnergy(GS* gs, const double* Rx, double
             if (PIGS_TRAP || r2 <= cP.rcut2) {
                 double r = sqrt(r2);
                 double dudr, d2u;
-                lk_exact_d1_d2<PIGS_WSM>(tW, r, dudr, d2u);
-                lap += __dadd_rn(__ddiv_rn(__dmul_rn((double)(cP.dim - 1), dudr), r), d2u);
-                F[0] += __ddiv_rn(__dmul_rn(dudr, d0), r);
-                F[1] += __ddiv_rn(__dmul_rn(dudr, d1), r);
-                F[2] += __ddiv_rn(__dmul_rn(dudr, d2), r);
-                pot += PIGS_VPAIR ? lk_exact_val<false>(cP.vtab, r) : lk_exact_val<PIGS_VSM>(tV, r);
+                lk_exact_d1_d2<PIGS_WSM>(tW, r, dudr, d2u);        // only u'' needs the reference's exact arithmetic
+                double q = dudr / r;
+                lap += fma((double)(cP.dim - 1), q, d2u);
+                F[0] += q * d0; F[1] += q * d1; F[2] += q * d2;
+                Lk k = lk_prep(r);
+                if (PIGS_TRAP) k.i0 = min(k.i0, cP.Nmax - 1);
+                pot += PIGS_VPAIR ? lk_val_pair(k) : lk_val<PIGS_VSM, 0, PIGS_VSM>(k);
             }
         }
         s[0] += F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
@@ -645,26 +646,45 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
                 one += 0.5 * xi[k] * xi[k] / a4;
             }
         }
-        for (int j = 0; j < cP.Np; ++j) {
-            if (j == i) continue;
-            double d0 = xi[0] - Rx[j], d1 = xi[1] - Ry[j], d2 = xi[2] - Rz[j];
-            if (!PIGS_TRAP) {
-                d0 = mimg(d0, cP.L[0], cP.Lh[0]); d1 = mimg(d1, cP.L[1], cP.Lh[1]); d2 = mimg(d2, cP.L[2], cP.Lh[2]);
-            }
-            double r2 = d0 * d0 + d1 * d1 + d2 * d2;
-            if (PIGS_TRAP || r2 <= cP.rcut2) {
-                double ir = rsqrt_pos(r2);
-                double r = r2 * ir;
-                Lk k = lk_prep(r);
-                if (PIGS_TRAP) k.i0 = min(k.i0, cP.Nmax - 1);
-                if (odd) {
+        if (odd) {
+            // forces are needed for every particle: particle i sums over all j (each pair is seen twice)
+            for (int j = 0; j < cP.Np; ++j) {
+                if (j == i) continue;
+                double d0 = xi[0] - Rx[j], d1 = xi[1] - Ry[j], d2 = xi[2] - Rz[j];
+                if (!PIGS_TRAP) {
+                    d0 = mimg_fast(d0, cP.L[0], cP.invL[0]); d1 = mimg_fast(d1, cP.L[1], cP.invL[1]); d2 = mimg_fast(d2, cP.L[2], cP.invL[2]);
+                }
+                double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+                if (PIGS_TRAP || r2 <= cP.rcut2) {
+                    double ir = rsqrt_pos(r2);
+                    double r = r2 * ir;
+                    Lk k = lk_prep(r);
+                    if (PIGS_TRAP) k.i0 = min(k.i0, cP.Nmax - 1);
                     double v, dv;
                     if (PIGS_VPAIR) lk_val_d1_pair(k, v, dv); else lk_val_d1<PIGS_VSM, 0, PIGS_VSM>(k, v, dv);
                     pot += v;
                     double q = dv * ir;
                     F[0] += q * d0; F[1] += q * d1; F[2] += q * d2;
-                } else {
-                    pot += PIGS_VPAIR ? lk_val_pair(k) : lk_val<PIGS_VSM, 0, PIGS_VSM>(k);
+                }
+            }
+        } else {
+            // potential only: every pair once -- particle i takes the partners (i+m) mod N, m = 1..N/2
+            // (for even N the m = N/2 pairs are taken from i < N/2 only); pot is doubled so that the common
+            // "half of the double-counted sum" below applies
+            const int half = cP.Np >> 1;
+            for (int m = 1; m <= half; ++m) {
+                if (!(cP.Np & 1) && m == half && i >= half) break;
+                int j = i + m; if (j >= cP.Np) j -= cP.Np;
+                double d0 = xi[0] - Rx[j], d1 = xi[1] - Ry[j], d2 = xi[2] - Rz[j];
+                if (!PIGS_TRAP) {
+                    d0 = mimg_fast(d0, cP.L[0], cP.invL[0]); d1 = mimg_fast(d1, cP.L[1], cP.invL[1]); d2 = mimg_fast(d2, cP.L[2], cP.invL[2]);
+                }
+                double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+                if (PIGS_TRAP || r2 <= cP.rcut2) {
+                    double ir = rsqrt_pos(r2);
+                    Lk k = lk_prep(r2 * ir);
+                    if (PIGS_TRAP) k.i0 = min(k.i0, cP.Nmax - 1);
+                    pot += 2.0 * (PIGS_VPAIR ? lk_val_pair(k) : lk_val<PIGS_VSM, 0, PIGS_VSM>(k));
                 }
             }
         }
