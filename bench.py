@@ -272,11 +272,7 @@ def run_ours(args, cfg):
             sim.sync()
             b = sim.get_block()[0]
         e2e_upd += float(sum(b["bead_updates"]))
-        Pn, xn, on, wn = sim.get_state_all()
-        hP.numpy()[...] = Pn
-        hX.numpy()[...] = xn
-        hO.numpy()[...] = on
-        hW.numpy()[...] = wn
+        sim.get_state_all(out=(hP.numpy(), hX.numpy(), hO.numpy(), hW.numpy()))     # straight into the pinned buffers
     barrier()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:

@@ -349,13 +349,20 @@ class PigsCuda:
         iw = np.zeros(n, dtype=np.int32) if iworm is None else np.ascontiguousarray(iworm, dtype=np.int32)
         self._ck(self.L.pigs_set_state_all(self.h, _dp(P), _dp(xe), _i32p(io), _i32p(iw)))
 
-    def get_state_all(self, want_path=True):
+    def get_state_all(self, want_path=True, out=None):
+        """All chains' state.  `out` = (Path, xend, isopen, iworm) caller buffers (e.g. pinned host memory)
+        to download into without intermediate copies."""
         n = self.n_chains
-        P = np.zeros((n,) + self.path_shape()) if want_path else None
-        xe = np.zeros((n, 2, self.dim))
-        io = np.zeros(n, dtype=np.int32)
-        iw = np.zeros(n, dtype=np.int32)
-        self._ck(self.L.pigs_get_state_all(self.h, _dp(P) if want_path else None, _dp(xe), _i32p(io), _i32p(iw)))
+        if out is not None:
+            P, xe, io, iw = out
+            assert P.flags.c_contiguous and P.dtype == np.float64 and P.size == n * int(np.prod(self.path_shape()))
+            assert xe.dtype == np.float64 and xe.size == n * 2 * self.dim and io.dtype == np.int32 and iw.dtype == np.int32
+        else:
+            P = np.zeros((n,) + self.path_shape()) if want_path else None
+            xe = np.zeros((n, 2, self.dim))
+            io = np.zeros(n, dtype=np.int32)
+            iw = np.zeros(n, dtype=np.int32)
+        self._ck(self.L.pigs_get_state_all(self.h, _dp(P) if P is not None else None, _dp(xe), _i32p(io), _i32p(iw)))
         return P, xe, io, iw
 
     def get_perm(self, chain):
