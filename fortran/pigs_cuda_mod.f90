@@ -31,7 +31,7 @@ type, bind(C) :: pigs_params
    integer(c_int32_t) :: CMFreq, sampling, Lstag, Nlev, Nstag, Nobdm, swapping
    integer(c_int32_t) :: n_chains, rng_mode
    integer(c_int64_t) :: seed
-   integer(c_int32_t) :: device, threads_per_chain, table_mode, reserved_
+   integer(c_int32_t) :: device, threads_per_chain, table_mode, action
 end type pigs_params
 
 ! struct pigs_block_result

@@ -87,7 +87,8 @@ typedef struct pigs_params {
     int32_t device;                    /* CUDA device ordinal */
     int32_t threads_per_chain;         /* 0 = auto; 32,64,128,256,512 */
     int32_t table_mode;                /* -1 = auto; 0 tables via L1/L2; 1 VTable in smem; 2 both in smem */
-    int32_t reserved_;
+    int32_t action;                    /* 0 = Chin (the live propagator, global_mod.f90:33-46), 1 = primitive
+                                          (the commented-out alternative, global_mod.f90:48,67) */
 } pigs_params;
 
 /* Raw block sums, summed over chains, exactly the quantities the driver holds

@@ -146,7 +146,7 @@ struct orc_sim {
     double Rm, a_ho[3];
     /* driver scalars (vpi.f90) */
     bool trap, crystal, swapping;
-    int sampling, seed, CMFreq, Lstag, Nlev, Nstag, Nobdm, Nk;
+    int sampling, seed, CMFreq, Lstag, Nlev, Nstag, Nobdm, Nk, action = 0;
     double density, dt, delta_cm;
     std::vector<double> Path, LogWF, VTable;
     double xend[2][3];                       /* xend(k,j) -> xend[j-1][k-1] */
@@ -179,6 +179,7 @@ struct orc_sim {
     /* global_mod.f90:19-72 */
     double GreenFunction(int opt, int ib, double dt_, double Pot, double F2) const {
         double g = 0.0;
+        if (action == 1) return opt == 0 ? dt_ * Pot : Pot;      /* global_mod.f90:48,67 (commented alternative) */
         if (opt == 0) {
             double Ve = Pot, Vc = Pot + dt_ * dt_ * F2 / 6.0;
             if (ib == 0) g = dt_ * Ve / 3.0;
@@ -1106,7 +1107,7 @@ orc_sim* orc_create(const orc_params* p) {
     s->sampling = p->sampling; s->Lstag = p->Lstag; s->Nlev = p->Nlev; s->Nstag = p->Nstag;
     s->Nbin = p->Nbin; s->Nk = p->Nk; s->swapping = p->swapping != 0; s->CWorm = p->CWorm;
     s->Nobdm = p->Nobdm; s->Npw = p->Npw; s->Nmax = p->Nmax;
-    s->wf_table = p->wf_table != 0; s->v_table = p->v_table != 0; s->Rm = p->Rm;
+    s->wf_table = p->wf_table != 0; s->v_table = p->v_table != 0; s->Rm = p->Rm; s->action = p->action;
     for (int k = 0; k < 3; ++k) { s->a_ho[k] = p->a_ho[k]; s->Lbox[k] = s->LboxHalf[k] = s->qbin[k] = 0.0; }
     const int dim = s->dim;
     /* vpi.f90:80-128 */

@@ -48,6 +48,9 @@ typedef struct orc_params {
     double  Rm;
     double  a_ho[3];
     double  Lbox_crystal[3];             /* used only when crystal != 0 (config_ini.in line 2) */
+    int32_t action;                      /* 0 = Chin (live code), 1 = primitive (the commented-out lines
+                                            global_mod.f90:48,67: GreenFunction = dt*Pot / Pot) */
+    int32_t pad_;
 } orc_params;
 
 /* Raw block sums exactly as the driver holds them at the end of the step

@@ -30,7 +30,7 @@ class OrcParams(C.Structure):
         ("Lstag", C.c_int32), ("Nlev", C.c_int32), ("Nstag", C.c_int32), ("Nbin", C.c_int32), ("Nk", C.c_int32),
         ("swapping", C.c_int32), ("CWorm", C.c_double), ("Nobdm", C.c_int32), ("Npw", C.c_int32),
         ("Nmax", C.c_int32), ("wf_table", C.c_int32), ("v_table", C.c_int32), ("Rm", C.c_double),
-        ("a_ho", C.c_double * 3), ("Lbox_crystal", C.c_double * 3),
+        ("a_ho", C.c_double * 3), ("Lbox_crystal", C.c_double * 3), ("action", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -157,7 +157,7 @@ class Oracle:
     DEFAULTS = dict(dim=3, Np=64, density=0.365, crystal=0, trap=0, dt=5e-3, Nb=15, seed=1982, delta_cm=0.12,
                     CMFreq=1, sampling="bis", Lstag=2, Nlev=1, Nstag=5, Nbin=100, Nk=50, swapping=0, CWorm=0.0,
                     Nobdm=0, Npw=0, Nmax=10000, wf_table=1, v_table=1, Rm=1.2, a_ho=(1.0, 1.0, 1.0),
-                    Lbox_crystal=(0.0, 0.0, 0.0))
+                    Lbox_crystal=(0.0, 0.0, 0.0), action=0)
 
     def __init__(self, cfg: dict, native: bool = False):
         self.L = _lib(native)

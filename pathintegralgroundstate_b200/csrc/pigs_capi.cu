@@ -147,6 +147,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     if (p->Lstag < 2) return fail(PIGS_E_ARG, "Lstag >= 2 required (OpenChain is attempted even when CWorm = 0)");
     if (p->Lstag > p->Nb) return fail(PIGS_E_ARG, "Lstag <= Nb required (OpenChain is attempted even when CWorm = 0)");
     if (p->rng_mode != PIGS_RNG_PHILOX && p->rng_mode != PIGS_RNG_MT_REPLAY) return fail(PIGS_E_ARG, "bad rng_mode");
+    if (p->action != 0 && p->action != 1) return fail(PIGS_E_ARG, "action must be 0 (Chin) or 1 (primitive)");
     if (!(p->dt > 0) || !(p->dr > 0) || !(p->rcut > 0)) return fail(PIGS_E_ARG, "dt, dr, rcut must be positive");
 
     int ndev = 0;
@@ -183,6 +184,16 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     P.rbin = p->rcut / (double)(float)p->Nbin;   // vpi.f90:128
     P.dt = p->dt; P.delta_cm = p->delta_cm; P.CWorm = p->CWorm; P.density = p->density;
     P.pi = std::acos(-1.0);
+    P.primitive = p->action == 1;
+    if (P.primitive) {
+        P.wS[0] = P.wS[1] = P.wS[2] = p->dt; P.cF = 0.0;
+        P.wE[0] = P.wE[1] = P.wE[2] = 1.0; P.cFE = 0.0;
+    } else {       // Chin (global_mod.f90:33-46, 52-65)
+        P.wS[0] = 2.0 * p->dt / 3.0; P.wS[1] = 4.0 * p->dt / 3.0; P.wS[2] = p->dt / 3.0;
+        P.cF = 4.0 * p->dt * p->dt * p->dt / 18.0;
+        P.wE[0] = 2.0 / 3.0; P.wE[1] = 4.0 / 3.0; P.wE[2] = 1.0 / 3.0;
+        P.cFE = (4.0 / 3.0) * (p->dt * p->dt * 0.5);
+    }
     P.logCd = std::log(p->CWorm * p->density);   // -inf when CWorm = 0: every open attempt is rejected (F8)
     P.seed = p->seed;
     P.chain_stride = (size_t)P.S * 3 * P.NpS;

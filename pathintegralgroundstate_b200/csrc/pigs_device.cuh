@@ -54,6 +54,10 @@ struct DevParams {
     int n_chains;
     double L[3], Lh[3], invL[3], qbin[3], a_ho[3];
     double rcut2, dr, inv_dr, rbin, dt, delta_cm, CWorm, density, pi, logCd;
+    // GreenFunction (global_mod.f90:19-72) as weights by slice class [even, odd, end]: action (opt 0) and its
+    // dt-derivative (opt 1); cF/cFE multiply |F|^2.  Chin: 2dt/3, 4dt/3, dt/3, cF = 4dt^3/18; primitive: dt, cF = 0.
+    double wS[3], cF, wE[3], cFE;
+    int primitive;
     unsigned long long seed;
     const double* logwf;      // (0:Nmax+1) in global memory
     const double* vtab;
@@ -464,7 +468,10 @@ __device__ __forceinline__ PairGeom pair_geom(bool valid, double x0, double x1, 
     return g;
 }
 
-__device__ __forceinline__ int bead_kind(int ib) { return (ib == 0 || ib == 2 * cP.Nb) ? 2 : (ib & 1); }
+// 0 interior slice without force term, 1 odd slice (Chin force term), 2 end slice (Jastrow)
+__device__ __forceinline__ int bead_kind(int ib) { return (ib == 0 || ib == 2 * cP.Nb) ? 2 : (cP.primitive ? 0 : (ib & 1)); }
+// counting class of a bead-update (even / odd / end), independent of the propagator
+__device__ __forceinline__ int bead_class(int ib) { return (ib == 0 || ib == 2 * cP.Nb) ? 2 : (ib & 1); }
 
 // coherent global load of a path coordinate (the path is written by this group
 // during the kernel, so no .nc; an explicit ld.global avoids the generic-address
@@ -555,11 +562,10 @@ PIGS_PRAGMA_UNROLL
 // (GreenFunction opt 0, global_mod.f90:29-46).
 __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
     const int kind = bead_kind(ib);
-    double dt = cP.dt;
-    if (kind == 2) return -v[1] + dt * v[0] / 3.0;
-    if (kind == 0) return 2.0 * dt * v[0] / 3.0;
+    if (kind == 2) return -v[1] + cP.wS[2] * v[0];
+    if (kind == 0) return cP.wS[ib & 1] * v[0];
     double f2 = (v[2] * v[2] + v[3] * v[3] + v[4] * v[4]) - (v[5] * v[5] + v[6] * v[6] + v[7] * v[7]);
-    return 4.0 * dt * (v[0] + dt * dt * f2 / 6.0) / 3.0;
+    return cP.wS[1] * v[0] + cP.cF * f2;
 }
 
 // One bead against partners j0, j0+jstride, ... by one warp.
@@ -574,7 +580,6 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
                                             const double (&xo)[3], const double (&xn)[3], int lane, double* part,
                                             const Partner& first) {
     const int kind = bead_kind(ib);
-    const double dt = cP.dt;
     double pot = 0.0, psi = 0.0, fn[3] = {0.0, 0.0, 0.0}, fo[3] = {0.0, 0.0, 0.0};
     if (TRAP && add_self) {
 #pragma unroll
@@ -590,14 +595,14 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
     pair_loop<TRAP, VSM, WSM, VPAIR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
     if (kind == 0) {
         double v = warp_sum(pot);
-        if (!part) return (2.0 * dt / 3.0) * v;
+        if (!part) return cP.wS[ib & 1] * v;
         if (lane < 8) part[lane] = (lane == 0) ? v : 0.0;
         return 0.0;
     }
     if (kind == 2) {
         double v = warp_sum2(pot, psi, lane);          // lanes 0..15: pot, lanes 16..31: psi
         if (!part) {
-            double t = (lane & 16) ? -v : (dt / 3.0) * v;
+            double t = (lane & 16) ? -v : cP.wS[2] * v;
             return t + shx(t, 16);
         }
         if (lane == 0) part[0] = v;
@@ -609,8 +614,8 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
     double v = warp_sum8(a, lane);                      // quad q holds value q
     const int q = lane >> 2;
     if (!part) {
-        const double c = 4.0 * dt * dt * dt / 18.0;
-        double t = (q == 0) ? (4.0 * dt / 3.0) * v : ((q == 1) ? 0.0 : ((q < 5) ? c * v * v : -c * v * v));
+        const double c = cP.cF;
+        double t = (q == 0) ? cP.wS[1] * v : ((q == 1) ? 0.0 : ((q < 5) ? c * v * v : -c * v * v));
         t += shx(t, 4); t += shx(t, 8); t += shx(t, 16);
         return t;
     }

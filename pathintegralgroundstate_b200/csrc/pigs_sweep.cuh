@@ -67,7 +67,7 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
                                                       double wlast) {
     const Grp G = grp();
     if (G.tid == 0) {
-        for (int m = 0; m < nb; ++m) gs->cnt[C_UPD_EVEN + bead_kind(b0 + m * bstride)] += 1;
+        for (int m = 0; m < nb; ++m) gs->cnt[C_UPD_EVEN + bead_class(b0 + m * bstride)] += 1;
     }
     const int nw = G.nwarps;
     int split = 1;
@@ -635,7 +635,7 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
         const double* Rx = slice(gs, ib);
         const double* Ry = Rx + cP.NpS;
         const double* Rz = Ry + cP.NpS;
-        const bool odd = ib & 1;
+        const bool odd = (ib & 1) && !cP.primitive;        // slices that need the force term
         double xi[3] = {Rx[i], Ry[i], Rz[i]};
         double F[3] = {0.0, 0.0, 0.0}, pot = 0.0, one = 0.0;
         if (PIGS_TRAP) {
@@ -689,9 +689,9 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
             }
         }
         double potsh = one + 0.5 * pot;                 // this particle's share of Pot(slice)
-        double w = (ib == 0) ? (1.0 / 3.0) : (odd ? (4.0 / 3.0) : (2.0 / 3.0));
+        double w = (ib == 0) ? cP.wE[2] : cP.wE[ib & 1];
         double e = w * potsh;
-        if (odd) e += (4.0 / 3.0) * (dt * dt * 0.5) * (F[0] * F[0] + F[1] * F[1] + F[2] * F[2]);
+        if (odd) e += cP.cFE * (F[0] * F[0] + F[1] * F[1] + F[2] * F[2]);
         if (ib == cP.Nb) s[1] += potsh;
         // kinetic link ib -> ib+1 (sample_mod.f90:359-380)
         const double* Nx = slice(gs, ib + 1);

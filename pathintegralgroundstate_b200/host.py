@@ -42,7 +42,7 @@ class PigsParams(C.Structure):
         ("CMFreq", C.c_int32), ("sampling", C.c_int32), ("Lstag", C.c_int32), ("Nlev", C.c_int32),
         ("Nstag", C.c_int32), ("Nobdm", C.c_int32), ("swapping", C.c_int32),
         ("n_chains", C.c_int32), ("rng_mode", C.c_int32), ("seed", C.c_uint64),
-        ("device", C.c_int32), ("threads_per_chain", C.c_int32), ("table_mode", C.c_int32), ("reserved_", C.c_int32),
+        ("device", C.c_int32), ("threads_per_chain", C.c_int32), ("table_mode", C.c_int32), ("action", C.c_int32),
     ]
 
 
@@ -192,6 +192,15 @@ def aziz_hfdhe2(r):
         return V0 * (A * np.exp(-alpha * d) - (C6 + C8 / d2 + C10 / d4) * Hx / d6)
 
 
+def lennard_jones(r):
+    """Lennard-Jones in reduced units, V0 (1/r^6 - 1)/r^6 with V0 = 22.0228 (the first commented-out
+    alternative, system_mod.f90:70-83)."""
+    r = np.asarray(r, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        r6 = r ** 6
+        return 22.0228 * (1.0 / r6 - 1.0) / r6
+
+
 def mcmillan_logpsi(r, Rm):
     """LogPsi(0,Rm,r) = -0.5 (Rm/r)**5 (system_mod.f90:38-66)."""
     r = np.asarray(r, dtype=np.float64)
@@ -200,17 +209,45 @@ def mcmillan_logpsi(r, Rm):
         return -0.5 * (q * q * q * q * q)
 
 
-def make_table(f, rmax: float, Nmax: int) -> np.ndarray:
+def make_table(f, rmax: float, Nmax: int, shift_free: bool = False) -> np.ndarray:
     """JastrowTable / PotentialTable (vpi_mod.f90:84-145): entry i holds f((i-1)*dr),
     i = 1..Nmax, pads F(0)=F(2), F(Nmax+1)=F(Nmax).  (The lookup then evaluates
-    f(r-dr); that shift is the reference's and is inherited on purpose.)"""
+    f(r-dr); that shift is the reference's and is inherited on purpose.)
+
+    shift_free=True is an input the reference lacks: entry i holds f(i*dr), so that
+    Interpolate(0,...) returns f(r) itself; the kernels are unchanged."""
     dr = rmax / _f32(Nmax - 1)
     F = np.zeros(Nmax + 2)
+    if shift_free:
+        i = np.arange(0, Nmax + 2)
+        F[:] = f(i * dr)
+        return F
     i = np.arange(1, Nmax + 1)
     F[1:Nmax + 1] = f((i - 1) * dr)
     F[0] = F[2]
     F[Nmax + 1] = F[Nmax]
     return F
+
+
+def write_config_ini(path: str, R, Lbox, density: float):
+    """config_ini.in as the driver and `init` read it (vpi.f90:101-107, vpi_mod.f90:220-228):
+    line 1 Np, line 2 Lbox(1:dim), line 3 density, then Np position lines."""
+    R = np.asarray(R, dtype=np.float64)
+    with open(path, "w") as f:
+        f.write(f"{R.shape[0]}\n")
+        f.write(" ".join(f"{x:.16e}" for x in Lbox[:R.shape[1]]) + "\n")
+        f.write(f"{density:.16e}\n")
+        for r in R:
+            f.write(" ".join(f"{x:.16e}" for x in r) + "\n")
+
+
+def read_config_ini(path: str, dim: int = 3):
+    with open(path) as f:
+        Np = int(f.readline().split()[0])
+        Lbox = [float(t.replace("d", "e").replace("D", "e")) for t in f.readline().split()[:dim]]
+        density = float(f.readline().split()[0].replace("d", "e").replace("D", "e"))
+        R = np.array([[float(t.replace("d", "e").replace("D", "e")) for t in f.readline().split()[:dim]] for _ in range(Np)])
+    return Np, Lbox, density, R
 
 
 def kn_ball(dim: int) -> float:
@@ -286,6 +323,7 @@ class PigsCuda:
         p.rng_mode = PIGS_RNG_MT_REPLAY if str(rng).lower().startswith("mt") else PIGS_RNG_PHILOX
         p.seed = int(cfg.get("seed", 1982) if seed is None else seed)
         p.device, p.threads_per_chain, p.table_mode = int(device), int(threads_per_chain), int(table_mode)
+        p.action = 1 if str(cfg.get("action", "chin")).lower().startswith("prim") else 0
         self.p = p
         self.dim, self.Np, self.Nb, self.Nmax = p.dim, p.Np, p.Nb, p.Nmax
         self.Nbin, self.Nk, self.Npw, self.n_chains = p.Nbin, p.Nk, p.Npw, p.n_chains
@@ -312,11 +350,11 @@ class PigsCuda:
         return (2 * self.Nb + 1, self.Np, self.dim)
 
     # -- JastrowTable / PotentialTable (vpi_mod.f90:84-145)
-    def fill_tables(self, potential="hfdb", Rm=None):
+    def fill_tables(self, potential="hfdb", Rm=None, shift_free=False):
         Rm = float(self.cfg["Rm"]) if Rm is None else Rm
-        pot = dict(hfdb=aziz_hfdb, hfdhe2=aziz_hfdhe2, zero=lambda r: np.zeros_like(r))[potential]
-        W = make_table(lambda r: mcmillan_logpsi(r, Rm), self.geo["rcut"], self.Nmax)
-        V = make_table(pot, self.geo["rcut"], self.Nmax)
+        pot = dict(hfdb=aziz_hfdb, hfdhe2=aziz_hfdhe2, lj=lennard_jones, zero=lambda r: np.zeros_like(r))[potential]
+        W = make_table(lambda r: mcmillan_logpsi(r, Rm), self.geo["rcut"], self.Nmax, shift_free)
+        V = make_table(pot, self.geo["rcut"], self.Nmax, shift_free)
         self.set_tables(W, V)
         return W, V
 

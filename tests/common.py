@@ -27,6 +27,8 @@ CS = dict(CWX, sampling="sta")
 
 def oracle_cfg(cfg):
     c = dict(cfg)
+    if "action" in c:
+        c["action"] = 1 if str(c["action"]).lower().startswith("prim") else 0
     if c.get("crystal") and "Lbox" in c:
         c["Lbox_crystal"] = list(c["Lbox"])
     for k in ("trap", "swapping", "wf_table", "v_table", "crystal"):

@@ -443,3 +443,29 @@ def test_many_chains_block_vector_is_the_sum_of_chains():
     g2.run_block(2)
     tot2, gr2, _, _ = g2.get_block()
     assert tot2 == tot and np.array_equal(gr, gr2)
+
+
+def test_primitive_action_option():
+    """the propagator the reference keeps as a commented-out line (global_mod.f90:48,67)"""
+    cfg = dict(CWX, action="primitive")
+    rng = np.random.default_rng(5)
+    o, g = make_pair(cfg)
+    S = 2 * cfg["Nb"] + 1
+    P = synthetic_path(cfg, rng)
+    n = 200
+    ibs = rng.integers(0, S, size=n).astype(np.int32)
+    ips = rng.integers(1, cfg["Np"] + 1, size=n).astype(np.int32)
+    R = P[ibs]
+    xold = R[np.arange(n), ips - 1].copy()
+    xnew = xold + rng.normal(0, 0.1, size=xold.shape)
+    ref = np.array([o.update_action(int(ips[i]), int(ibs[i]), xnew[i], xold[i], R=R[i]) for i in range(n)])
+    assert close(g.update_action(R, ips, ibs, xnew, xold), ref)
+    # DeltaS = dt * DeltaV on interior slices, whatever their parity
+    o2, _ = make_pair(CWX)
+    i = int(np.flatnonzero((ibs % 2 == 0) & (ibs > 0) & (ibs < S - 1))[0])
+    chin = o2.update_action(int(ips[i]), int(ibs[i]), xnew[i], xold[i], R=R[i])
+    assert ref[i] == pytest.approx(1.5 * chin, rel=1e-12)          # dt vs 2dt/3
+    ref_e = np.array([o.therm_energy(P)])
+    E, Ec, Ep = g.therm_energy(P[None])
+    assert close(np.array([[E[0], Ec[0], Ep[0]]]), ref_e)
+    _replay_block(cfg, nchain=2, nstep=8, nblock=1)

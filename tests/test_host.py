@@ -171,3 +171,29 @@ def test_two_rank_gloo_block_reduction(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GLOO_OK 2" in outs[0]
+
+
+def test_inputs_the_reference_lacks(tmp_path):
+    from pathintegralgroundstate_b200 import lennard_jones, write_config_ini, read_config_ini
+    from pathintegralgroundstate_b200.statistics import mean_and_error, blocking, jackknife
+    # LJ (system_mod.f90:70-83): zero at r = 1, minimum -V0/4 at r = 2^(1/6)
+    assert lennard_jones(1.0) == 0.0 and lennard_jones(2 ** (1 / 6)) == pytest.approx(-22.0228 / 4, rel=1e-12)
+    # shift-free tables: Interpolate(0,...) returns f(r) instead of f(r - dr)
+    from oracle.pigs_oracle import interpolate, potential
+    g = derive_geometry(C2)
+    V = make_table(aziz_hfdb, g["rcut"], 10000, shift_free=True)
+    assert interpolate(0, V, g["dr"], 1.5) == pytest.approx(potential(1.5), rel=1e-6)
+    # config_ini.in round trip, hcp cell
+    R, L = hcp_lattice()
+    write_config_ini(tmp_path / "config_ini.in", R, L, 0.48426)
+    Np, L2, rho, R2 = read_config_ini(tmp_path / "config_ini.in")
+    assert Np == 180 and np.allclose(L2, L) and rho == 0.48426 and np.allclose(R2, R, atol=1e-15)
+    # statistics
+    rng = np.random.default_rng(0)
+    x = rng.normal(3.0, 2.0, 4000)
+    m, e = mean_and_error(x)
+    assert abs(m - 3.0) < 4 * e and e == pytest.approx(2.0 / np.sqrt(4000), rel=0.1)
+    bl = blocking(x)
+    assert bl[0][0] == 1 and abs(bl[-1][1] - bl[0][1]) < 0.5 * bl[0][1]          # white noise: flat blocking curve
+    jm, je = jackknife(x)
+    assert jm == pytest.approx(x.mean()) and je == pytest.approx(e, rel=0.05)
