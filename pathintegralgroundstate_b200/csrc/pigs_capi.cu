@@ -133,6 +133,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     if (!p || !out) return fail(PIGS_E_ARG, "null argument");
     *out = nullptr;
     if (p->dim < 1 || p->dim > 3) return fail(PIGS_E_ARG, "dim must be 1..3");
+    if (2 * p->Nb + 1 > MAXS) return fail(PIGS_E_ARG, "Nb too large (2*Nb+1 must not exceed 132)");
     if (p->Np < 2 || p->Nb < 1 || p->Nmax < 4 || p->n_chains < 1) return fail(PIGS_E_ARG, "Np>=2, Nb>=1, Nmax>=4, n_chains>=1 required");
     if (p->Nbin < 1 || p->Nk < 0 || p->Npw < 0) return fail(PIGS_E_ARG, "bad Nbin/Nk/Npw");
     if (p->sampling != 0 && p->sampling != 1) return fail(PIGS_E_ARG, "sampling must be 0 ('sta') or 1 ('bis')");
@@ -194,6 +195,12 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
         P.wE[0] = 2.0 / 3.0; P.wE[1] = 4.0 / 3.0; P.wE[2] = 1.0 / 3.0;
         P.cFE = (4.0 / 3.0) * (p->dt * p->dt * 0.5);
     }
+    for (int n = 0; n < MAXS; ++n) {
+        P.sig_free[n] = std::sqrt((double)(float)n * p->dt);
+        P.sig_stage[n] = std::sqrt((double)((float)n / (float)(n + 1)) * p->dt);
+    }
+    for (int l = 0; l < 16; ++l) P.sig_bis[l] = std::sqrt(0.5 * (0.5 * (double)(float)(1 << l) * p->dt));
+    P.half_inv_dt2 = 0.5 / (p->dt * p->dt);
     P.logCd = std::log(p->CWorm * p->density);   // -inf when CWorm = 0: every open attempt is rejected (F8)
     P.seed = p->seed;
     P.chain_stride = (size_t)P.S * 3 * P.NpS;

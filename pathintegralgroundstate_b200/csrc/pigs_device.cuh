@@ -37,6 +37,7 @@
 
 namespace pigs {
 
+constexpr int MAXS = 132;   // 2*Nb+1 <= MAXS (Nb <= 65)
 constexpr int NE = 12;      // energy sums
 constexpr int NCNT = 24;    // int64 counters, same order as pigs_block_result
 enum Cnt {
@@ -58,6 +59,12 @@ struct DevParams {
     // dt-derivative (opt 1); cF/cFE multiply |F|^2.  Chin: 2dt/3, 4dt/3, dt/3, cF = 4dt^3/18; primitive: dt, cF = 0.
     double wS[3], cF, wE[3], cFE;
     int primitive;
+    // proposal widths, precomputed on the host with the reference's arithmetic (no sqrt/div in the kernel):
+    //   sig_free[L]  = sqrt(real(L)*dt)                        free end of a length-L move  (vpi_mod.f90:632)
+    //   sig_stage[n] = sqrt((real(n)/real(n+1))*dt), float32 ratio (Q15)                    (vpi_mod.f90:531)
+    //   sig_bis[l]   = sqrt(0.5*(0.5*real(2**l)*dt))           bisection, delta_ib = 2**l     (vpi_mod.f90:906-907)
+    double sig_free[MAXS], sig_stage[MAXS], sig_bis[16];
+    double half_inv_dt2;
     unsigned long long seed;
     const double* logwf;      // (0:Nmax+1) in global memory
     const double* vtab;

@@ -240,7 +240,7 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
                     double xold = so(gs, k, iend), g = sn(gs, k, iend), anc = sn(gs, k, ianc), base;
                     if (flags & MV_FREE_NEXT) base = xold - wrap_lt<VAR>(k, xold - anc);
                     else base = xold + wrap_lt<VAR>(k, anc - xold);
-                    sn(gs, k, iend) = bc_wrap<VAR>(k, base + sqrt((double)L * cP.dt) * g);
+                    sn(gs, k, iend) = bc_wrap<VAR>(k, base + cP.sig_free[L] * g);
                 }
                 if (type == MV_BRIDGE) {      // Levy bridge ii -> ie (vpi_mod.f90:509-549)
                     double pnext = sn(gs, k, ie), pprev = sn(gs, k, ii);
@@ -249,7 +249,7 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
                         double xold = so(gs, k, ib), g = sn(gs, k, ib);
                         double xprev = xold + wrap_lt<VAR>(k, pprev - xold);
                         double xnext = xold - wrap_lt<VAR>(k, xold - pnext);
-                        double sigma = sqrt((double)((float)(L - j) / (float)(L - j + 1)) * cP.dt);   // float32 ratio (Q15)
+                        double sigma = cP.sig_stage[L - j];                                           // float32 ratio (Q15)
                         double xmid = (xnext + xprev * (double)(L - j)) / (double)(L - j + 1);
                         pprev = bc_wrap<VAR>(k, xmid + sigma * g);
                         sn(gs, k, ib) = pprev;
@@ -258,7 +258,7 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
             }
             gsync();
         } else if (type == MV_BISECT) {      // one bisection level (vpi_mod.f90:905-956)
-            double sigma = sqrt(0.5 * (0.5 * (double)delta_ib * cP.dt));
+            const double sigma = cP.sig_bis[Nl - lev + 1];        // delta_ib = 2^(Nl-lev+1)
             for (int i = G.tid; i < nb * dim; i += G.size) {
                 int j = div_dim(i), k = i - j * dim;
                 int iprev = ii + j * delta_ib, inext = iprev + delta_ib, icurr = (iprev + inext) >> 1;
@@ -700,7 +700,7 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
             l0 = mimg(l0, cP.L[0], cP.Lh[0]); l1 = mimg(l1, cP.L[1], cP.Lh[1]); l2 = mimg(l2, cP.L[2], cP.Lh[2]);
         }
         double lr2 = l0 * l0 + l1 * l1 + l2 * l2;
-        if (PIGS_TRAP || lr2 <= cP.rcut2) e -= 0.5 * lr2 / (dt * dt);
+        if (PIGS_TRAP || lr2 <= cP.rcut2) e -= lr2 * cP.half_inv_dt2;
         s[0] += e;
     }
     group_sum<2>(gs, s);
