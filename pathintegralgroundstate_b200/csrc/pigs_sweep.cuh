@@ -67,7 +67,15 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
                                                       double wlast) {
     const Grp G = grp();
     if (G.tid == 0) {
-        for (int m = 0; m < nb; ++m) gs->cnt[C_UPD_EVEN + bead_class(b0 + m * bstride)] += 1;
+        // bead-update counters by slice class, in closed form (beads b0, b0+bstride, ...)
+        const int last = b0 + (nb - 1) * bstride;
+        const int nend = (b0 == 0 ? 1 : 0) + ((last == 2 * cP.Nb && last != 0) ? 1 : 0) - ((nb == 1 && b0 == 0 && last == 2 * cP.Nb) ? 1 : 0);
+        int nodd;
+        if (bstride & 1) nodd = ((last + 1) >> 1) - (b0 >> 1);
+        else nodd = (b0 & 1) ? nb : 0;
+        gs->cnt[C_UPD_END] += nend;
+        gs->cnt[C_UPD_ODD] += nodd;
+        gs->cnt[C_UPD_EVEN] += nb - nodd - nend;
     }
     const int nw = G.nwarps;
     int split = 1;
