@@ -393,25 +393,39 @@ __device__ __forceinline__ double u01_from(unsigned lo, unsigned hi) {        //
     return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// Per-thread view of the chain's Philox stream (group-uniform by construction):
+// the 64-bit draw counter plus the unused 32-bit words of the last block, so one
+// Philox4x32 call serves four uniforms (the reference's grnd() has 32 bits too).
+struct RngS {
+    unsigned long long ctr;
+    unsigned w0, w1, w2;
+    int nleft;
+};
 // one uniform, identical in every thread of the group
 template <bool MT>
-__device__ __forceinline__ double rng_uniform(GS* gs, unsigned long long& ctr) {
+__device__ __forceinline__ double rng_uniform(GS* gs, RngS& st) {
     if (MT) {
         gsync();
         if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) gs->bc[0] = mt_grnd(gs);
         gsync();
         return gs->bc[0];
     } else {
-        uint4 r = philox_at(ctr, (unsigned)gs->chain);
-        ctr += 1;
-        return u01_from(r.x, r.y);
+        unsigned x;
+        if (st.nleft == 0) {
+            uint4 r = philox_at(st.ctr, (unsigned)gs->chain);
+            st.ctr += 1;
+            x = r.x; st.w0 = r.y; st.w1 = r.z; st.w2 = r.w; st.nleft = 3;
+        } else {
+            x = st.w0; st.w0 = st.w1; st.w1 = st.w2; st.nleft -= 1;
+        }
+        return (double)x * 2.3283064365386963e-10;        // x / 2^32 in [0,1)
     }
 }
 // unit Gaussians for beads b0 + j*bstride (j<nb), components k<dim, written into
 // seg_new[k*S + bead] in the reference's draw order (bead-major, component-minor).
 // Ends with a group sync.
 template <bool MT>
-__device__ __forceinline__ void rng_gauss_fill(GS* gs, unsigned long long* pctr, int dim, int b0, int bstride, int nb) {
+__device__ __forceinline__ void rng_gauss_fill(GS* gs, RngS* pst, int dim, int b0, int bstride, int nb) {
     const Grp G = grp();
     const int n = nb * dim;
     double* dst = seg_new(gs);
@@ -423,7 +437,7 @@ __device__ __forceinline__ void rng_gauss_fill(GS* gs, unsigned long long* pctr,
             }
         }
     } else {
-        unsigned long long ctr = *pctr;
+        unsigned long long ctr = pst->ctr;
         for (int i = G.tid; i < n; i += G.size) {
             int j = dim == 3 ? (i * 43691) >> 17 : (dim == 2 ? i >> 1 : i), k = i - j * dim;
             uint4 r = philox_at(ctr + (unsigned long long)i, (unsigned)gs->chain);
@@ -431,7 +445,7 @@ __device__ __forceinline__ void rng_gauss_fill(GS* gs, unsigned long long* pctr,
             double u2 = u01_from(r.z, r.w);
             dst[k * cP.S + b0 + j * bstride] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
         }
-        *pctr = ctr + (unsigned long long)n;
+        pst->ctr = ctr + (unsigned long long)n;
     }
     gsync();
 }

@@ -27,7 +27,7 @@
 
 namespace pigs {
 
-typedef unsigned long long ull;
+typedef RngS ull;      // the RNG stream state threaded through the moves
 
 // (measured: making the action evaluation a real call costs 35% -- call-site spills;
 // it stays inlined into the move engine)
@@ -946,7 +946,8 @@ PIGS_T __device__ __forceinline__ void sweep_body() {
         }
         if (tid < NE) gs->eacc[tid] = 0.0;
         if (tid < NCNT) gs->cnt[tid] = 0;
-        ull ctr = cP.pctr[c];
+        ull ctr;
+        ctr.ctr = cP.pctr[c]; ctr.w0 = ctr.w1 = ctr.w2 = 0u; ctr.nleft = 0;
         gsync();
 
         if (cA.op == OP_BLOCK) {
@@ -988,7 +989,7 @@ PIGS_T __device__ __forceinline__ void sweep_body() {
             ist[IS_OPEN] = gs->isopen; ist[IS_IWORM] = gs->iworm0 + 1; ist[IS_IPERM] = gs->iperm;
             ist[IS_NEWPC] = gs->new_pc; ist[IS_ENDPC] = gs->end_pc; ist[IS_IK] = gs->ik0 + 1; ist[IS_IDIAG_AUX] = gs->idiag_aux;
             ist[IS_MTI] = gs->mti;
-            cP.pctr[c] = ctr;
+            cP.pctr[c] = ctr.ctr;
         }
         gsync();
     }
