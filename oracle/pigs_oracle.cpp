@@ -989,15 +989,18 @@ struct orc_sim {
                     else particle_already_in_cycle = false;
                 }
                 if (end_perm_cycle == false) {
-                    if (!particle_already_in_cycle) {
-                        iperm = iperm + 1;
+                    if (!particle_already_in_cycle && iperm < Np) {      /* (iperm < Np always holds for a consistent state) */
+                        iperm = iperm < 0 ? 1 : iperm + 1;
                         Particles_in_perm_cycle[iperm - 1] = ikk;
                     }
                 }
             }
         }
         if (end_perm_cycle) {
-            Perm_histogram[iperm - 1] = Perm_histogram[iperm - 1] + 1;
+            /* an open worm set from outside without its permutation record has iperm = 0: the reference would
+               index Perm_histogram(0) (out of bounds); both this oracle and the CUDA path count it as length 1 */
+            int len = iperm < 1 ? 1 : (iperm > Np ? Np : iperm);
+            Perm_histogram[len - 1] = Perm_histogram[len - 1] + 1;
             if (isopen) {
                 std::fill(Particles_in_perm_cycle.begin(), Particles_in_perm_cycle.end(), 0);
                 Particles_in_perm_cycle[0] = iw;

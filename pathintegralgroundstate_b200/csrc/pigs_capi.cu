@@ -304,7 +304,11 @@ static int put_scalars(pigs_ctx* h, int chain0, int nchain, const double* xend, 
     std::vector<int> ist((size_t)nchain * IS_N);
     CK(cudaMemcpyAsync(ist.data(), h->d_istate + (size_t)chain0 * IS_N, ist.size() * sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
-    for (int c = 0; c < nchain; ++c) { ist[(size_t)c * IS_N + IS_OPEN] = isopen[c] != 0; ist[(size_t)c * IS_N + IS_IWORM] = iworm[c]; }
+    for (int c = 0; c < nchain; ++c) {
+        if (isopen[c] && (iworm[c] < 1 || iworm[c] > h->P.Np)) return fail(PIGS_E_ARG, "isopen needs 1 <= iworm <= Np");
+        ist[(size_t)c * IS_N + IS_OPEN] = isopen[c] != 0;
+        ist[(size_t)c * IS_N + IS_IWORM] = (iworm[c] >= 0 && iworm[c] <= h->P.Np) ? iworm[c] : 0;
+    }
     CK(cudaMemcpyAsync(h->d_istate + (size_t)chain0 * IS_N, ist.data(), ist.size() * sizeof(int), cudaMemcpyHostToDevice, h->st));
     CK(cudaStreamSynchronize(h->st));
     return PIGS_OK;
@@ -371,6 +375,7 @@ extern "C" int pigs_set_perm(pigs_handle h, int chain, int iperm, const int32_t*
     int ist[IS_N];
     CK(cudaMemcpyAsync(ist, h->d_istate + (size_t)chain * IS_N, sizeof ist, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
+    if (iperm < 0 || iperm > h->P.Np) return fail(PIGS_E_ARG, "iperm must be in 0..Np");
     ist[IS_IPERM] = iperm; ist[IS_NEWPC] = new_pc != 0; ist[IS_ENDPC] = end_pc != 0;
     CK(cudaMemcpyAsync(h->d_istate + (size_t)chain * IS_N, ist, sizeof ist, cudaMemcpyHostToDevice, h->st));
     if (cycle) CK(cudaMemcpyAsync(h->d_cyc + (size_t)chain * h->P.Np, cycle, sizeof(int) * h->P.Np, cudaMemcpyHostToDevice, h->st));
@@ -402,6 +407,7 @@ extern "C" int pigs_get_mt(pigs_handle h, int chain, uint32_t* mt624, int32_t* m
 extern "C" int pigs_set_mt(pigs_handle h, int chain, const uint32_t* mt624, int32_t mti) {
     NEED(h); NEED_CHAIN(h, chain);
     if (!mt624) return fail(PIGS_E_ARG, "null mt state");
+    if (mti < 0 || mti > 625) return fail(PIGS_E_ARG, "mti must be in 0..625");
     int v = mti;
     CK(cudaMemcpyAsync(h->d_mt + (size_t)chain * 624, mt624, 624 * sizeof(unsigned), cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(h->d_istate + (size_t)chain * IS_N + IS_MTI, &v, sizeof(int), cudaMemcpyHostToDevice, h->st));

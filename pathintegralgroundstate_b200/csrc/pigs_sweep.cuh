@@ -530,13 +530,16 @@ static __device__ __noinline__ void PermutationSampling(GS* gs, bool have_swap) 
         if (have_swap && gs->swap_acc) {
             bool found = false;
             for (int i = 0; i < cP.Np; ++i) if (cyc[i] == gs->ik0 + 1) { found = true; break; }
-            if (!gs->end_pc && !found) {
-                gs->iperm += 1;
+            if (!gs->end_pc && !found && gs->iperm < cP.Np) {
+                gs->iperm = gs->iperm < 0 ? 1 : gs->iperm + 1;
                 cyc[gs->iperm - 1] = gs->ik0 + 1;
             }
         }
         if (gs->end_pc) {
-            hist[gs->iperm - 1] += 1;
+            // a worm uploaded as open without its permutation record has iperm = 0 (the reference would index
+            // Perm_histogram(0)); count it as a cycle of length 1
+            int len = gs->iperm < 1 ? 1 : (gs->iperm > cP.Np ? cP.Np : gs->iperm);
+            hist[len - 1] += 1;
             if (gs->isopen) {
                 for (int i = 0; i < cP.Np; ++i) cyc[i] = 0;
                 cyc[0] = gs->iworm0 + 1;
