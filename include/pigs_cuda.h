@@ -154,7 +154,7 @@ int  pigs_get_block(pigs_handle h, pigs_block_result* out, double* gr, double* S
 /* same for one chain */
 int  pigs_get_block_chain(pigs_handle h, int chain, pigs_block_result* out, double* gr, double* Sk, double* nrho);
 /* device pointer + length (doubles) of the chain-summed accumulator vector of
- * the last block, laid out [12 energy sums | 27 counters as doubles | gr | Sk |
+ * the last block, laid out [12 energy sums | 24 counters as doubles | gr | Sk |
  * nrho]; for an in-place NCCL all-reduce by the caller (multi-GPU). */
 int  pigs_block_vector(pigs_handle h, double** dev_ptr, int* n);
 /* unpack such a vector (host copy, e.g. after the all-reduce) */

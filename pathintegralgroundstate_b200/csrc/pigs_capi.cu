@@ -28,7 +28,7 @@ static int fail(int code, const std::string& m) { g_err = m; return code; }
 struct pigs_ctx {
     pigs_params hp;
     DevParams P;
-    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32, prefetch = 2;
+    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32, prefetch = 3;
     size_t smem = 0;
     int nvec = 0;
     bool tables_set = false;

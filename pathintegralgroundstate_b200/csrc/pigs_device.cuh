@@ -91,7 +91,7 @@ struct SweepArgs {
     int chain_only;      // >=0: only that chain (OP_UNIFORM/OP_GAUSS/OP_SEED)
     int seed;            // OP_SEED
     int groups_per_cta, threads_per_chain, tshift;   // T = 1 << tshift
-    int prefetch;        // issue L1 prefetches of a move's slices at move start
+    int prefetch;        // 0 off, 1 L1 line prefetch at move start, 2 L2 bulk per phase, 3 L2 bulk rolling (default)
     int* accepted;       // OP_MOVE [n_chains]
     int* aux;            // OP_MOVE [n_chains]
     double* draws;       // OP_UNIFORM/OP_GAUSS [n]

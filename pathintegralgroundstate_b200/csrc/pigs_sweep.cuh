@@ -64,7 +64,7 @@ __device__ __forceinline__ int div_dim(int i) {          // i / cP.dim for dim i
 // partners of a bead are divided over `split` warps and combined through smem.
 template <int VAR>
 static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, int bstride, int nb, double wfirst,
-                                                      double wlast) {
+                                                      double wlast, bool roll) {
     const Grp G = grp();
     if (G.tid == 0) {
         // bead-update counters by slice class, in closed form (beads b0, b0+bstride, ...)
@@ -104,6 +104,10 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         for (int k = 0; k < 3; ++k) { xo[k] = so(gs, k, ib); xn[k] = sn(gs, k, ib); }
         const Partner cur = first;
         const int tn = task + nw;
+        if (roll && G.lane == 0 && s == 0) {       // rolling L2 prefetch: the slice this warp reads two tasks from now
+            const int m2 = m + ((split > 1) ? 2 * (nw / split) : 2 * nw);
+            if (m2 < nb) prefetch_slice_L2(slice(gs, b0 + m2 * bstride));
+        }
         if (tn < ntask) {
             int mn = (split > 1) ? tn / split : tn, sn_ = (split > 1) ? tn - mn * split : 0;
             if (sn_ * 32 + G.lane < cP.Np) first = load_partner(slice(gs, b0 + mn * bstride), sn_ * 32 + G.lane);
@@ -184,6 +188,17 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
     const int L = ie - ii;
     const int dim = cP.dim;
     if (cA.prefetch == 1) prefetch_slices(gs->path, (type == MV_TRANSLATE) ? ii : m0, ((type == MV_TRANSLATE) ? ie : m1) - ((type == MV_TRANSLATE) ? ii : m0) + 1, G.tid, G.size);
+    if (cA.prefetch == 3) {
+        // L2 prefetch schedule: the first slices a move evaluates are requested here, before the segment is even
+        // read; later ones one bisection level ahead (below) or two beads ahead (rolling, inside eval_action), so
+        // at most a few slices per chain are in flight and the L2 working set of all resident chains stays small.
+        if (type == MV_BISECT) {
+            if (G.tid == 0) prefetch_slice_L2(slice(gs, (flags & (MV_FREE_NEXT | MV_FREE_PREV)) ? ((flags & MV_FREE_NEXT) ? ii : ie) : ii + (L >> 1)));
+        } else {
+            const int nfirst = min(2 * G.nwarps, m1 - m0 + 1);
+            if (G.tid < nfirst) prefetch_slice_L2(slice(gs, m0 + G.tid));
+        }
+    }
     if (half) {
         if (G.tid < dim) pth(gs, G.tid, ip0, cP.Nb) = gs->xend[(half - 1) * 3 + G.tid];
         gsync();
@@ -232,6 +247,10 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
             else { b0 = ii + (delta_ib >> 1); bs = delta_ib; nb = 1 << (lev - 1); }
         } else { b0 = m0; bs = 1; nb = m1 - m0 + 1; }
         if (cA.prefetch == 2 && G.tid < nb) prefetch_slice_L2(slice(gs, b0 + G.tid * bs));
+        if (cA.prefetch == 3 && type == MV_BISECT && ph + 1 < nphase) {        // one level ahead
+            const int lev1 = ph + 1 + (has_free ? 0 : 1), d1 = 1 << (Nl - lev1 + 1);
+            if (G.tid < (1 << (lev1 - 1))) prefetch_slice_L2(slice(gs, ii + (d1 >> 1) + G.tid * d1));
+        }
         if (MT) {      // the reference's draw order (Appendix A of SURVEY.md)
             if (type == MV_BRIDGE) {
                 if (flags & MV_FREE_PREV) { rng_gauss_fill<MT>(gs, &ctr, dim, ie, 1, 1); rng_gauss_fill<MT>(gs, &ctr, dim, ii + 1, 1, L - 1); }
@@ -279,7 +298,8 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
         }
         // ---- action
         const double wf = (flags & MV_WFIRST_HALF) ? 0.5 : 1.0, wl = (flags & MV_WLAST_HALF) ? 0.5 : 1.0;
-        double S = eval_action<VAR>(gs, ip0, b0, bs, nb, (type == MV_BISECT) ? 1.0 : wf, (type == MV_BISECT) ? 1.0 : wl);
+        double S = eval_action<VAR>(gs, ip0, b0, bs, nb, (type == MV_BISECT) ? 1.0 : wf, (type == MV_BISECT) ? 1.0 : wl,
+                                    cA.prefetch == 3 && type != MV_BISECT);
         if (type != MV_BISECT) {
             S += Sbase;
             if (flags & MV_DK_OLD_ADD) S += DeltaK;
