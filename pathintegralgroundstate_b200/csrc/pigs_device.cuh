@@ -570,19 +570,24 @@ template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
 __device__ __forceinline__ void pair_loop(int kind, const double* Rx, int ip0, int j0, int jstride, const double (&xo)[3],
                                           const double (&xn)[3], Partner nxt, double& pot, double& psi, double (&fn)[3],
                                           double (&fo)[3]) {
+    // running pointer + countdown: no per-iteration address arithmetic, no loop-invariant reloads
+    const double* p = Rx + j0;
+    const long long sy = cP.NpS;
+    const int self_left = cP.Np - ip0;
 PIGS_PRAGMA_UNROLL
-    for (int j = j0; j < cP.Np; j += jstride) {
+    for (int left = cP.Np - j0; left > 0; left -= jstride) {
         const Partner cur = nxt;
-        const int jn = j + jstride;
-        if (jn < cP.Np) nxt = load_partner(Rx, jn);
-        pair_body<TRAP, VSM, WSM, VPAIR>(kind, j != ip0, cur, xo, xn, pot, psi, fn, fo);
+        p += jstride;
+        if (left > jstride) { nxt.x = ldpath(p); nxt.y = ldpath(p + sy); nxt.z = ldpath(p + 2 * sy); }
+        pair_body<TRAP, VSM, WSM, VPAIR>(kind, left != self_left, cur, xo, xn, pot, psi, fn, fo);
     }
 }
 
 // DeltaS of UpdateAction from the eight reduced values [pot, psi, Fnew(3), Fold(3)]
 // (GreenFunction opt 0, global_mod.f90:29-46).
 __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
-    const int kind = bead_kind(ib);
+    int kind = bead_kind(ib);
+    asm volatile("" : "+r"(kind));      // opaque: keeps the class in a register instead of re-deriving it from ib every iteration
     if (kind == 2) return -v[1] + cP.wS[2] * v[0];
     if (kind == 0) return cP.wS[ib & 1] * v[0];
     double f2 = (v[2] * v[2] + v[3] * v[3] + v[4] * v[4]) - (v[5] * v[5] + v[6] * v[6] + v[7] * v[7]);
@@ -600,7 +605,8 @@ template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
 __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, int j0, int jstride, bool add_self,
                                             const double (&xo)[3], const double (&xn)[3], int lane, double* part,
                                             const Partner& first) {
-    const int kind = bead_kind(ib);
+    int kind = bead_kind(ib);
+    asm volatile("" : "+r"(kind));      // opaque: keeps the class in a register instead of re-deriving it from ib every iteration
     double pot = 0.0, psi = 0.0, fn[3] = {0.0, 0.0, 0.0}, fo[3] = {0.0, 0.0, 0.0};
     if (TRAP && add_self) {
 #pragma unroll
