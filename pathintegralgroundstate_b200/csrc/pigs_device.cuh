@@ -121,6 +121,18 @@ __device__ __forceinline__ void gsync() {
 }
 
 // per-group state in shared memory: header + arrays
+// Move descriptor + RNG state parked in shared memory across the partner loop
+// (run_move, pigs_sweep.cuh); ctr ping-pongs by phase parity.
+struct RngS {
+    unsigned long long ctr;
+    unsigned w0, w1, w2;
+    int nleft;
+};
+struct MovePark {
+    RngS ctr[2];
+    double Sbase, DeltaK;
+    int flags, ip0, ii, ie, m0, m1, pad0, pad1;
+};
 struct GS {
     double* path;        // this chain
     double* xend;        // this chain, [2][3]
@@ -136,6 +148,7 @@ struct GS {
     int ibc[8];
     // chain state (written by thread 0, read by all after a group sync)
     int mti, isopen, iworm0, iperm, new_pc, end_pc, ik0, swap_acc, idiag_aux, chain, pad0, pad1;
+    MovePark pk;
     // followed by: seg_old[3S] seg_new[3S] part[np*8] pp[Np]
 };
 __host__ __device__ inline int part_slots(int nwarps) { return nwarps < 4 ? 4 : nwarps; }
@@ -396,11 +409,6 @@ __device__ __forceinline__ double u01_from(unsigned lo, unsigned hi) {        //
 // Per-thread view of the chain's Philox stream (group-uniform by construction):
 // the 64-bit draw counter plus the unused 32-bit words of the last block, so one
 // Philox4x32 call serves four uniforms (the reference's grnd() has 32 bits too).
-struct RngS {
-    unsigned long long ctr;
-    unsigned w0, w1, w2;
-    int nleft;
-};
 // one uniform, identical in every thread of the group
 template <bool MT>
 __device__ __forceinline__ double rng_uniform(GS* gs, RngS& st) {

@@ -179,8 +179,43 @@ enum MoveFlags {
 };
 // [m0,m1] = beads evaluated and, on acceptance, committed.  Returns acceptance
 // (group-uniform).  seg_old/seg_new stay valid for the caller's epilogue.
-PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags, int ip0, int ii, int ie, int m0, int m1,
-                                                    double Sbase) {
+//
+// Register budget: the partner loop inside eval_action wants every register of
+// the 128 a thread has (16 warps/SM), so nothing of the move's own state is
+// allowed to stay live across it.  The move descriptor and the RNG state are
+// parked in the group's shared-memory block (gs->pk) by the prologue; each phase
+// is pre (reads pk, draws, proposes) -> eval_action -> post (reads pk, Metropolis),
+// with compiler memory barriers on both sides of the evaluation so the values
+// are re-read instead of carried.  All threads of a group hold identical copies,
+// so the parked words are written with identical values by all of them; the RNG
+// state, the only word that changes, ping-pongs between two slots by phase
+// parity (a thread ahead by less than one group sync never overwrites the slot
+// a slower thread still has to read).
+struct PhaseGeom {
+    int type, L, Nl, nphase, lev, delta_ib, b0, bs, nb, iend, ianc;
+    bool has_free, gate;
+};
+__device__ __forceinline__ PhaseGeom phase_geom(int flags, int ii, int ie, int m0, int m1, int ph) {
+    PhaseGeom g;
+    g.type = flags & MV_TYPE_MASK;
+    g.L = ie - ii;
+    g.has_free = flags & (MV_FREE_NEXT | MV_FREE_PREV);
+    g.iend = (flags & MV_FREE_NEXT) ? ii : ie;
+    g.ianc = (flags & MV_FREE_NEXT) ? ie : ii;
+    g.Nl = 31 - __clz(g.L);                                          // bisection: L = 2^Nl
+    g.nphase = (g.type == MV_BISECT) ? g.Nl + (g.has_free ? 1 : 0) : 1;
+    g.gate = (g.type == MV_BISECT) && g.has_free && ph == 0;         // free end of Move{Head,Tail}Bisection
+    g.lev = (g.type == MV_BISECT) ? ph + (g.has_free ? 0 : 1) : 0;   // 1..Nl
+    g.delta_ib = (g.type == MV_BISECT && !g.gate) ? (1 << (g.Nl - g.lev + 1)) : 2;
+    if (g.type == MV_BISECT) {
+        if (g.gate) { g.b0 = g.iend; g.bs = 1; g.nb = 1; }
+        else { g.b0 = ii + (g.delta_ib >> 1); g.bs = g.delta_ib; g.nb = 1 << (g.lev - 1); }
+    } else { g.b0 = m0; g.bs = 1; g.nb = m1 - m0 + 1; }
+    return g;
+}
+
+PIGS_T __device__ __forceinline__ void move_prologue(GS* gs, ull* pctr, int flags, int ip0, int ii, int ie, int m0, int m1,
+                                                     double Sbase) {
     const Grp G = grp();
     ull ctr = *pctr;
     const int type = flags & MV_TYPE_MASK;
@@ -190,8 +225,8 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
     if (cA.prefetch == 1) prefetch_slices(gs->path, (type == MV_TRANSLATE) ? ii : m0, ((type == MV_TRANSLATE) ? ie : m1) - ((type == MV_TRANSLATE) ? ii : m0) + 1, G.tid, G.size);
     if (cA.prefetch == 3) {
         // L2 prefetch schedule: the first slices a move evaluates are requested here, before the segment is even
-        // read; later ones one bisection level ahead (below) or two beads ahead (rolling, inside eval_action), so
-        // at most a few slices per chain are in flight and the L2 working set of all resident chains stays small.
+        // read; later ones one bisection level ahead (phase_pre) or two beads ahead (rolling, inside eval_action),
+        // so at most a few slices per chain are in flight and the L2 working set of all resident chains stays small.
         if (type == MV_BISECT) {
             if (G.tid == 0) prefetch_slice_L2(slice(gs, (flags & (MV_FREE_NEXT | MV_FREE_PREV)) ? ((flags & MV_FREE_NEXT) ? ii : ie) : ii + (L >> 1)));
         } else {
@@ -229,101 +264,138 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
     }
     double DeltaK = 0.0;
     if (flags & MV_DK_OLD_ADD) DeltaK = link_DeltaK<VAR>(seg_old(gs), ii, ie, L);
-    const bool has_free = flags & (MV_FREE_NEXT | MV_FREE_PREV);
-    const int iend = (flags & MV_FREE_NEXT) ? ii : ie, ianc = (flags & MV_FREE_NEXT) ? ie : ii;
     // beads that need Gaussians: interior + free end
     const int g0 = (flags & MV_FREE_NEXT) ? ii : ii + 1, g1 = (flags & MV_FREE_PREV) ? ie : ie - 1;
     if (!MT && type != MV_TRANSLATE) rng_gauss_fill<MT>(gs, &ctr, dim, g0, 1, g1 - g0 + 1);     // Philox: one pass per move
-    const int Nl = 31 - __clz(L);                                  // bisection: L = 2^Nl
-    const int nphase = (type == MV_BISECT) ? Nl + (has_free ? 1 : 0) : 1;
-    bool accept = true;
-    for (int ph = 0; ph < nphase; ++ph) {
-        const bool gate = (type == MV_BISECT) && has_free && ph == 0;          // free end of Move{Head,Tail}Bisection
-        const int lev = (type == MV_BISECT) ? ph + (has_free ? 0 : 1) : 0;     // 1..Nl
-        const int delta_ib = (type == MV_BISECT && !gate) ? (1 << (Nl - lev + 1)) : 2;
-        int b0, bs, nb;
-        if (type == MV_BISECT) {
-            if (gate) { b0 = iend; bs = 1; nb = 1; }
-            else { b0 = ii + (delta_ib >> 1); bs = delta_ib; nb = 1 << (lev - 1); }
-        } else { b0 = m0; bs = 1; nb = m1 - m0 + 1; }
-        if (cA.prefetch == 2 && G.tid < nb) prefetch_slice_L2(slice(gs, b0 + G.tid * bs));
-        if (cA.prefetch == 3 && type == MV_BISECT && ph + 1 < nphase) {        // one level ahead
-            const int lev1 = ph + 1 + (has_free ? 0 : 1), d1 = 1 << (Nl - lev1 + 1);
-            if (G.tid < (1 << (lev1 - 1))) prefetch_slice_L2(slice(gs, ii + (d1 >> 1) + G.tid * d1));
+    MovePark& pk = gs->pk;
+    pk.ctr[0] = ctr;
+    pk.Sbase = Sbase; pk.DeltaK = DeltaK;
+    pk.flags = flags; pk.ip0 = ip0; pk.ii = ii; pk.ie = ie; pk.m0 = m0; pk.m1 = m1;
+}
+
+// proposal of phase ph; returns the beads to evaluate and their end weights
+PIGS_T __device__ __forceinline__ void phase_pre(GS* gs, int ph, int& b0, int& bs, int& nb, double& wf, double& wl, bool& roll) {
+    const Grp G = grp();
+    const MovePark& pk = gs->pk;
+    const int flags = pk.flags, ii = pk.ii, ie = pk.ie;
+    const PhaseGeom g = phase_geom(flags, ii, ie, pk.m0, pk.m1, ph);
+    const int type = g.type, L = g.L, dim = cP.dim;
+    b0 = g.b0; bs = g.bs; nb = g.nb;
+    if (cA.prefetch == 2 && G.tid < nb) prefetch_slice_L2(slice(gs, b0 + G.tid * bs));
+    if (cA.prefetch == 3 && type == MV_BISECT && ph + 1 < g.nphase) {        // one level ahead
+        const int lev1 = ph + 1 + (g.has_free ? 0 : 1), d1 = 1 << (g.Nl - lev1 + 1);
+        if (G.tid < (1 << (lev1 - 1))) prefetch_slice_L2(slice(gs, ii + (d1 >> 1) + G.tid * d1));
+    }
+    if (MT) {      // the reference's draw order (Appendix A of SURVEY.md); the MT state lives in HBM, not in ctr
+        ull dummy;
+        if (type == MV_BRIDGE) {
+            const int g0 = (flags & MV_FREE_NEXT) ? ii : ii + 1, g1 = (flags & MV_FREE_PREV) ? ie : ie - 1;
+            if (flags & MV_FREE_PREV) { rng_gauss_fill<MT>(gs, &dummy, dim, ie, 1, 1); rng_gauss_fill<MT>(gs, &dummy, dim, ii + 1, 1, L - 1); }
+            else rng_gauss_fill<MT>(gs, &dummy, dim, g0, 1, g1 - g0 + 1);
+        } else if (type == MV_BISECT) {
+            rng_gauss_fill<MT>(gs, &dummy, dim, b0, bs, nb);
         }
-        if (MT) {      // the reference's draw order (Appendix A of SURVEY.md)
-            if (type == MV_BRIDGE) {
-                if (flags & MV_FREE_PREV) { rng_gauss_fill<MT>(gs, &ctr, dim, ie, 1, 1); rng_gauss_fill<MT>(gs, &ctr, dim, ii + 1, 1, L - 1); }
-                else rng_gauss_fill<MT>(gs, &ctr, dim, g0, 1, g1 - g0 + 1);
-            } else if (type == MV_BISECT) {
-                rng_gauss_fill<MT>(gs, &ctr, dim, b0, bs, nb);
+    }
+    if (type == MV_BRIDGE || g.gate) {
+        if (G.tid < dim) {
+            const int k = G.tid;
+            if (g.has_free) {      // xnew = BC(unwrap(anchor) + sigma*g)    (vpi_mod.f90:619-645 / 758-785)
+                double xold = so(gs, k, g.iend), gz = sn(gs, k, g.iend), anc = sn(gs, k, g.ianc), base;
+                if (flags & MV_FREE_NEXT) base = xold - wrap_lt<VAR>(k, xold - anc);
+                else base = xold + wrap_lt<VAR>(k, anc - xold);
+                sn(gs, k, g.iend) = bc_wrap<VAR>(k, base + cP.sig_free[L] * gz);
             }
-        }
-        // ---- proposal
-        if (type == MV_BRIDGE || gate) {
-            if (G.tid < dim) {
-                const int k = G.tid;
-                if (has_free) {      // xnew = BC(unwrap(anchor) + sigma*g)    (vpi_mod.f90:619-645 / 758-785)
-                    double xold = so(gs, k, iend), g = sn(gs, k, iend), anc = sn(gs, k, ianc), base;
-                    if (flags & MV_FREE_NEXT) base = xold - wrap_lt<VAR>(k, xold - anc);
-                    else base = xold + wrap_lt<VAR>(k, anc - xold);
-                    sn(gs, k, iend) = bc_wrap<VAR>(k, base + cP.sig_free[L] * g);
+            if (type == MV_BRIDGE) {      // Levy bridge ii -> ie (vpi_mod.f90:509-549)
+                double pnext = sn(gs, k, ie), pprev = sn(gs, k, ii);
+                for (int j = 1; j <= L - 1; ++j) {
+                    int ib = ii + j;
+                    double xold = so(gs, k, ib), gz = sn(gs, k, ib);
+                    double xprev = xold + wrap_lt<VAR>(k, pprev - xold);
+                    double xnext = xold - wrap_lt<VAR>(k, xold - pnext);
+                    double sigma = cP.sig_stage[L - j];                                           // float32 ratio (Q15)
+                    double xmid = (xnext + xprev * (double)(L - j)) / (double)(L - j + 1);
+                    pprev = bc_wrap<VAR>(k, xmid + sigma * gz);
+                    sn(gs, k, ib) = pprev;
                 }
-                if (type == MV_BRIDGE) {      // Levy bridge ii -> ie (vpi_mod.f90:509-549)
-                    double pnext = sn(gs, k, ie), pprev = sn(gs, k, ii);
-                    for (int j = 1; j <= L - 1; ++j) {
-                        int ib = ii + j;
-                        double xold = so(gs, k, ib), g = sn(gs, k, ib);
-                        double xprev = xold + wrap_lt<VAR>(k, pprev - xold);
-                        double xnext = xold - wrap_lt<VAR>(k, xold - pnext);
-                        double sigma = cP.sig_stage[L - j];                                           // float32 ratio (Q15)
-                        double xmid = (xnext + xprev * (double)(L - j)) / (double)(L - j + 1);
-                        pprev = bc_wrap<VAR>(k, xmid + sigma * g);
-                        sn(gs, k, ib) = pprev;
-                    }
-                }
-            }
-            gsync();
-        } else if (type == MV_BISECT) {      // one bisection level (vpi_mod.f90:905-956)
-            const double sigma = cP.sig_bis[Nl - lev + 1];        // delta_ib = 2^(Nl-lev+1)
-            for (int i = G.tid; i < nb * dim; i += G.size) {
-                int j = div_dim(i), k = i - j * dim;
-                int iprev = ii + j * delta_ib, inext = iprev + delta_ib, icurr = (iprev + inext) >> 1;
-                double xold = so(gs, k, icurr), g = sn(gs, k, icurr);
-                double xprev = xold + wrap_lt<VAR>(k, sn(gs, k, iprev) - xold);
-                double xnext = xold - wrap_lt<VAR>(k, xold - sn(gs, k, inext));
-                sn(gs, k, icurr) = bc_wrap<VAR>(k, 0.5 * (xprev + xnext) + sigma * g);
-            }
-            gsync();
-        }
-        // ---- action
-        const double wf = (flags & MV_WFIRST_HALF) ? 0.5 : 1.0, wl = (flags & MV_WLAST_HALF) ? 0.5 : 1.0;
-        double S = eval_action<VAR>(gs, ip0, b0, bs, nb, (type == MV_BISECT) ? 1.0 : wf, (type == MV_BISECT) ? 1.0 : wl,
-                                    cA.prefetch == 3 && type != MV_BISECT);
-        if (type != MV_BISECT) {
-            S += Sbase;
-            if (flags & MV_DK_OLD_ADD) S += DeltaK;
-            if (flags & MV_DK_NEW_SUB) S -= link_DeltaK<VAR>(seg_new(gs), ii, ie, L);
-        }
-        // ---- the Metropolis question (e.g. vpi_mod.f90:356-364): a uniform is consumed only if exp(-S)<1
-        if (!(S <= 0.0)) {
-            double e = exp(-S);
-            if (!(e >= 1.0)) {                     // NaN falls through: rejected after its draw (Q23)
-                double u = uniform<MT, VAR>(gs, ctr);
-                if (!(e >= u)) { accept = false; break; }
             }
         }
         gsync();
+    } else if (type == MV_BISECT) {      // one bisection level (vpi_mod.f90:905-956)
+        const double sigma = cP.sig_bis[g.Nl - g.lev + 1];        // delta_ib = 2^(Nl-lev+1)
+        for (int i = G.tid; i < nb * dim; i += G.size) {
+            int j = div_dim(i), k = i - j * dim;
+            int iprev = ii + j * g.delta_ib, inext = iprev + g.delta_ib, icurr = (iprev + inext) >> 1;
+            double xold = so(gs, k, icurr), gz = sn(gs, k, icurr);
+            double xprev = xold + wrap_lt<VAR>(k, sn(gs, k, iprev) - xold);
+            double xnext = xold - wrap_lt<VAR>(k, xold - sn(gs, k, inext));
+            sn(gs, k, icurr) = bc_wrap<VAR>(k, 0.5 * (xprev + xnext) + sigma * gz);
+        }
+        gsync();
     }
-    if (accept) {
-        const int c0 = (type == MV_TRANSLATE) ? ii : m0, n = ((type == MV_TRANSLATE) ? ie : m1) - c0 + 1;
-        for (int i = G.tid; i < 3 * n; i += G.size) {
-            int k = (i >= n) + (i >= 2 * n), ib = c0 + (i - k * n);
-            if (k < dim) pth(gs, k, ip0, ib) = sn(gs, k, ib);
+    wf = (type != MV_BISECT && (flags & MV_WFIRST_HALF)) ? 0.5 : 1.0;
+    wl = (type != MV_BISECT && (flags & MV_WLAST_HALF)) ? 0.5 : 1.0;
+    roll = cA.prefetch == 3 && type != MV_BISECT;
+}
+
+// the Metropolis question of phase ph: 0 = go on with the next phase, 1 = rejected, 2 = accepted (last phase)
+PIGS_T __device__ __forceinline__ int phase_post(GS* gs, int ph, double S) {
+    MovePark& pk = gs->pk;
+    const int flags = pk.flags, ii = pk.ii, ie = pk.ie;
+    const int type = flags & MV_TYPE_MASK;
+    ull ctr = pk.ctr[ph & 1];
+    if (type != MV_BISECT) {
+        S += pk.Sbase;
+        if (flags & MV_DK_OLD_ADD) S += pk.DeltaK;
+        if (flags & MV_DK_NEW_SUB) S -= link_DeltaK<VAR>(seg_new(gs), ii, ie, ie - ii);
+    }
+    // (e.g. vpi_mod.f90:356-364): a uniform is consumed only if exp(-S)<1
+    bool accept = true;
+    if (!(S <= 0.0)) {
+        double e = exp(-S);
+        if (!(e >= 1.0)) {                     // NaN falls through: rejected after its draw (Q23)
+            double u = uniform<MT, VAR>(gs, ctr);
+            if (!(e >= u)) accept = false;
         }
     }
+    pk.ctr[(ph + 1) & 1] = ctr;
+    if (!accept) return 1;
     gsync();
-    *pctr = ctr;
+    const PhaseGeom g = phase_geom(flags, ii, ie, 0, 0, ph);
+    return (ph + 1 == g.nphase) ? 2 : 0;
+}
+
+PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags, int ip0, int ii, int ie, int m0, int m1,
+                                                    double Sbase) {
+    move_prologue<MT, VAR>(gs, pctr, flags, ip0, ii, ie, m0, m1, Sbase);
+    int ph = 0, r;
+    for (;; ++ph) {
+        int b0, bs, nb;
+        double wf, wl;
+        bool roll;
+        asm volatile("" ::: "memory");
+        phase_pre<MT, VAR>(gs, ph, b0, bs, nb, wf, wl, roll);
+        const int ipp = gs->pk.ip0;
+        asm volatile("" ::: "memory");
+        const double S = eval_action<VAR>(gs, ipp, b0, bs, nb, wf, wl, roll);
+        asm volatile("" ::: "memory");
+        r = phase_post<MT, VAR>(gs, ph, S);
+        if (r) break;
+    }
+    asm volatile("" ::: "memory");
+    const Grp G = grp();
+    const MovePark& pk = gs->pk;
+    const bool accept = (r == 2);
+    if (accept) {
+        const int type = pk.flags & MV_TYPE_MASK, ip1 = pk.ip0, dim = cP.dim;
+        const int c0 = (type == MV_TRANSLATE) ? pk.ii : pk.m0, n = ((type == MV_TRANSLATE) ? pk.ie : pk.m1) - c0 + 1;
+        for (int i = G.tid; i < 3 * n; i += G.size) {
+            int k = (i >= n) + (i >= 2 * n), ib = c0 + (i - k * n);
+            if (k < dim) pth(gs, k, ip1, ib) = sn(gs, k, ib);
+        }
+    }
+    const ull cfin = pk.ctr[(ph + 1) & 1];
+    gsync();
+    *pctr = cfin;
     return accept;
 }
 
