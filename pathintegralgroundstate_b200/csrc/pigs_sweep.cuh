@@ -364,8 +364,17 @@ PIGS_T __device__ __forceinline__ int phase_post(GS* gs, int ph, double S) {
     return (ph + 1 == g.nphase) ? 2 : 0;
 }
 
-PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags, int ip0, int ii, int ie, int m0, int m1,
-                                                    double Sbase) {
+// The engine proper.  It is instantiated exactly twice per kernel: inlined into
+// the kernel body at the single call site of the diagonal sweep (diag_sweep,
+// >95% of all moves), and once as the out-of-line run_move below for the rare
+// callers (worm and half-chain moves, unit calls).  The inlined copy matters:
+// ptxas compiles a loop inside an ABI callee markedly worse than the same loop
+// inside the kernel function -- loop-invariant constants are re-read from the
+// constant bank every iteration and the global-load descriptor is re-copied
+// into uniform registers before every load (the isolated partner loop,
+// scripts/loopbench*.cu, runs 17% slower behind a __noinline__ wrapper).
+PIGS_T __device__ __forceinline__ bool run_move_body(GS* gs, ull* pctr, int flags, int ip0, int ii, int ie, int m0, int m1,
+                                                     double Sbase) {
     move_prologue<MT, VAR>(gs, pctr, flags, ip0, ii, ie, m0, m1, Sbase);
     int ph = 0, r;
     for (;; ++ph) {
@@ -397,6 +406,10 @@ PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags
     gsync();
     *pctr = cfin;
     return accept;
+}
+PIGS_T static __device__ __noinline__ bool run_move(GS* gs, ull* pctr, int flags, int ip0, int ii, int ie, int m0, int m1,
+                                                    double Sbase) {
+    return run_move_body<MT, VAR>(gs, pctr, flags, ip0, ii, ie, m0, m1, Sbase);
 }
 
 // ---------------------------------------------------------------- the 14 moves as descriptors
@@ -875,28 +888,45 @@ static __device__ __noinline__ void OBDM(const double* xend, double* nrho) {
 }
 
 // ---------------------------------------------------------------- driver schedule
-PIGS_T __device__ __noinline__ void diag_sweep(GS* gs, ull* pctr, int istep, int skip0) {       // vpi.f90:329-366 / 412-439
-    if (istep % cP.CMFreq == 0) {
-        for (int ip = 0; ip < cP.Np; ++ip) {
-            if (ip == skip0) continue;
+// The diagonal sweep as ONE loop over its moves with ONE call site of the
+// engine (see run_move_body): translate every chain (every CMFreq steps), then
+// Nstag passes of {head, tail, middle} per particle.  Same order, same draws and
+// same counters as the nested loops of the driver; the wrappers of the section
+// above (TranslateChain, MoveHead, ...) restate the same descriptors for the
+// unit calls.
+PIGS_T __device__ __forceinline__ void diag_sweep(GS* gs, ull* pctr, int istep, int skip0) {       // vpi.f90:329-366 / 412-439
+    const int Np = cP.Np, twoNb = 2 * cP.Nb;
+    const bool bis = cP.sampling != 0;
+    const int nT = (istep % cP.CMFreq == 0) ? Np : 0;
+    const int total = nT + cP.Nstag * Np * 3;
+    int sub = nT ? 0 : 1, ip = 0;            // sub: 0 translate, 1 head, 2 tail, 3 middle
+    for (int q = 0; q < total; ++q) {
+        const int cs = sub, cip = ip;
+        if (sub == 0) { if (++ip == Np) { ip = 0; sub = 1; } }
+        else if (sub == 3) { sub = 1; if (++ip == Np) ip = 0; }
+        else ++sub;
+        if (cip == skip0) continue;
+        int flags, ii, ie, m0, m1, cacc;
+        if (cs == 0) {                        // TranslateChain
             bump(gs, C_TRY_CM);
-            TranslateChain<MT, VAR>(gs, pctr, ip);
-        }
-    }
-    for (int istag = 0; istag < cP.Nstag; ++istag) {
-        for (int ip = 0; ip < cP.Np; ++ip) {
-            if (ip == skip0) continue;
-            bump(gs, C_TRY_STAG);
-            if (cP.sampling == 0) {
-                MoveHead<MT, VAR>(gs, pctr, cP.Lstag, ip, 0);
-                MoveTail<MT, VAR>(gs, pctr, cP.Lstag, ip, 0);
-                Staging<MT, VAR>(gs, pctr, cP.Lstag, ip);
-            } else {
-                EndBisection<MT, VAR>(gs, pctr, cP.Nlev, ip, true);
-                EndBisection<MT, VAR>(gs, pctr, cP.Nlev, ip, false);
-                Bisection<MT, VAR>(gs, pctr, cP.Nlev, ip);
+            flags = MV_TRANSLATE; ii = 0; ie = twoNb; m0 = 0; m1 = twoNb; cacc = C_ACC_CM;
+        } else {
+            if (cs == 1) bump(gs, C_TRY_STAG);
+            const int Lm = bis ? (1 << cP.Nlev) : cP.Lstag;
+            ull ctr = *pctr;
+            const int d = draw_int<MT, VAR>(gs, ctr, (cs == 3) ? twoNb - Lm + 1 : (bis ? cP.Nlev : cP.Lstag) - 1);
+            *pctr = ctr;
+            const int Ls = bis ? (1 << (d + 2)) : d + 2;      // length of an end move
+            const int ty = bis ? MV_BISECT : MV_BRIDGE;
+            if (cs == 1) {                    // MoveHead / MoveHeadBisection
+                flags = ty | MV_FREE_NEXT; ii = 0; ie = Ls; m0 = 0; m1 = ie - 1; cacc = C_ACC_HEAD;
+            } else if (cs == 2) {             // MoveTail / MoveTailBisection
+                flags = ty | MV_FREE_PREV; ie = twoNb; ii = ie - Ls; m0 = ii + 1; m1 = ie; cacc = C_ACC_TAIL;
+            } else {                          // Staging / Bisection
+                flags = ty; ii = d; ie = ii + Lm; m0 = ii + 1; m1 = ie - 1; cacc = C_ACC_BD;
             }
         }
+        if (run_move_body<MT, VAR>(gs, pctr, flags, cip, ii, ie, m0, m1, 0.0)) bump(gs, cacc);
     }
 }
 PIGS_T __device__ __forceinline__ void mc_step(GS* gs, ull* pctr, int istep) {      // vpi.f90:297-475
@@ -926,9 +956,14 @@ PIGS_T __device__ __forceinline__ void mc_step(GS* gs, ull* pctr, int istep) {  
     }
     *pctr = ctr;
     gsync();
-    if (gs->isopen) {
+    const bool is_open = gs->isopen;
+    if (!is_open) {
+        if (G.tid == 0) gs->idiag_aux += 1;
+        bump(gs, C_IDIAG);
+    }
+    diag_sweep<MT, VAR>(gs, pctr, istep, is_open ? gs->iworm0 : -1);       // the one inlined instance of the engine
+    if (is_open) {
         const int iw = gs->iworm0;
-        diag_sweep<MT, VAR>(gs, pctr, istep, iw);
         for (int iobdm = 0; iobdm < cP.Nobdm; ++iobdm) {
             for (int j = 1; j <= 2; ++j) {
                 bump(gs, C_TRY_CM_HALF);
@@ -948,9 +983,6 @@ PIGS_T __device__ __forceinline__ void mc_step(GS* gs, ull* pctr, int istep) {  
             if (!PIGS_TRAP) { OBDM(gs->xend, gs->acc + cP.off_nr); gsync(); }
         }
     } else {
-        if (G.tid == 0) gs->idiag_aux += 1;
-        bump(gs, C_IDIAG);
-        diag_sweep<MT, VAR>(gs, pctr, istep, -1);
         double e1[3], e2[3], et[3];
         LocalEnergy<VAR>(gs, slice(gs, 0), e1);
         LocalEnergy<VAR>(gs, slice(gs, 2 * cP.Nb), e2);
