@@ -28,7 +28,7 @@ static int fail(int code, const std::string& m) { g_err = m; return code; }
 struct pigs_ctx {
     pigs_params hp;
     DevParams P;
-    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32, prefetch = 3;
+    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32, prefetch = 3, pfdist = 2;
     size_t smem = 0;
     int nvec = 0;
     bool tables_set = false;
@@ -58,6 +58,7 @@ static SweepArgs base_args(pigs_ctx* h) {
     A.tshift = 0;
     while ((1 << A.tshift) < h->T) ++A.tshift;
     A.prefetch = h->prefetch;
+    A.pfdist = h->pfdist;
     return A;
 }
 static int launch(pigs_ctx* h, const SweepArgs& A) {
@@ -164,6 +165,8 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     {
         const char* e = getenv("PIGS_PREFETCH");      // tuning knob (default on)
         if (e) h->prefetch = atoi(e);
+        e = getenv("PIGS_PFDIST");
+        if (e && atoi(e) >= 1) h->pfdist = atoi(e);
     }
     DevParams& P = h->P;
     std::memset(&P, 0, sizeof P);

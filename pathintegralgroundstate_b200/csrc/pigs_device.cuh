@@ -92,6 +92,7 @@ struct SweepArgs {
     int seed;            // OP_SEED
     int groups_per_cta, threads_per_chain, tshift;   // T = 1 << tshift
     int prefetch;        // 0 off, 1 L1 line prefetch at move start, 2 L2 bulk per phase, 3 L2 bulk rolling (default)
+    int pfdist;          // rolling distance in beads (PIGS_PFDIST)
     int* accepted;       // OP_MOVE [n_chains]
     int* aux;            // OP_MOVE [n_chains]
     double* draws;       // OP_UNIFORM/OP_GAUSS [n]
@@ -586,7 +587,11 @@ PIGS_PRAGMA_UNROLL
     for (int left = cP.Np - j0; left > 0; left -= jstride) {
         const Partner cur = nxt;
         p += jstride;
+#ifdef PIGS_BLOCKED_TEST
+        if (left > jstride) { const double* pb = Rx + 96 * ((p - Rx) >> 5) + ((p - Rx) & 31); nxt.x = ldpath(pb); nxt.y = ldpath(pb + 32); nxt.z = ldpath(pb + 64); }
+#else
         if (left > jstride) { nxt.x = ldpath(p); nxt.y = ldpath(p + sy); nxt.z = ldpath(p + 2 * sy); }
+#endif
         pair_body<TRAP, VSM, WSM, VPAIR>(kind, left != self_left, cur, xo, xn, pot, psi, fn, fo);
     }
 }

@@ -105,7 +105,7 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         const Partner cur = first;
         const int tn = task + nw;
         if (roll && G.lane == 0 && s == 0) {       // rolling L2 prefetch: the slice this warp reads two tasks from now
-            const int m2 = m + ((split > 1) ? 2 * (nw / split) : 2 * nw);
+            const int m2 = m + cA.pfdist * ((split > 1) ? (nw / split) : nw);
             if (m2 < nb) prefetch_slice_L2(slice(gs, b0 + m2 * bstride));
         }
         if (tn < ntask) {
@@ -230,7 +230,7 @@ PIGS_T __device__ __forceinline__ void move_prologue(GS* gs, ull* pctr, int flag
         if (type == MV_BISECT) {
             if (G.tid == 0) prefetch_slice_L2(slice(gs, (flags & (MV_FREE_NEXT | MV_FREE_PREV)) ? ((flags & MV_FREE_NEXT) ? ii : ie) : ii + (L >> 1)));
         } else {
-            const int nfirst = min(2 * G.nwarps, m1 - m0 + 1);
+            const int nfirst = min(cA.pfdist * G.nwarps, m1 - m0 + 1);
             if (G.tid < nfirst) prefetch_slice_L2(slice(gs, m0 + G.tid));
         }
     }

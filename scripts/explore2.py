@@ -5,6 +5,7 @@ for c in cases:
     env = dict(os.environ)
     if c.get("lib"): env["PIGS_LIB"] = os.path.abspath(c["lib"])
     env["PIGS_PREFETCH"] = str(c.get("pf", 1))
+    if "pfd" in c: env["PIGS_PFDIST"] = str(c["pfd"])
     r = subprocess.run([sys.executable, "scripts/prof_case.py", c["cfg"], str(c["n"]), str(c["T"]), str(c["tm"]), str(c.get("nstep", 2)), "1"],
                        env=env, capture_output=True, text=True)
     print(json.dumps(c), "=>", r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "ERR " + r.stderr[-300:], flush=True)

@@ -21,6 +21,17 @@ __global__ void __launch_bounds__(512, 1) k_loop(const double* slices, int nslic
     for (int it = 0; it < iters; ++it) {
         h = h * 1664525u + 1013904223u;
         int s = (h >> 8) % nslices;
+#if defined(PF_BULK) || defined(PF_LINE)
+        {   // prefetch the slice of the NEXT iteration (one bead ahead)
+            unsigned h2 = h * 1664525u + 1013904223u;
+            const double* Rn = slices + (size_t)((h2 >> 8) % nslices) * ss;
+#ifdef PF_BULK
+            if (lane == 0) prefetch_slice_L2(Rn);
+#else
+            for (int l = lane; l < (int)(ss * 8 / 128); l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(Rn) + l * 128));
+#endif
+        }
+#endif
         const double* Rx = slices + (size_t)s * ss;
         int ip0 = (h >> 3) % cP.Np;
         int ib = KINDSEL == 0 ? 2 : (KINDSEL == 1 ? 3 : (KINDSEL == 2 ? 0 : 1 + (int)((h >> 20) % 29)));
