@@ -1,0 +1,82 @@
+// Isolated benchmark of the pair loop (bead_eval) of libpigs_cuda: one warp per "chain", random slices
+// from a big buffer (HBM-resident like production) or a small one (L2-resident).  Not part of the product.
+#include "../pathintegralgroundstate_b200/csrc/pigs_device.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+using namespace pigs;
+
+static __device__ __noinline__ double wrapped(const double* Rx, int ip0, int ib, int lane, const double (&xo)[3], const double (&xn)[3], const Partner& first) {
+    return bead_eval<false, true, true, false>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn, lane, nullptr, first);
+}
+static __device__ __noinline__ unsigned other_work(unsigned h, double* out) {
+    for (int i = 0; i < (int)(h & 3); ++i) h = h * 1664525u + (unsigned)__double2int_rn(sqrt((double)(h >> 12)));
+    if (h == 12345u) out[0] = 1.0;
+    return h;
+}
+template <int KINDSEL>
+__global__ void __launch_bounds__(512, 1) k_loop(const double* slices, int nslices, int iters, double* out) {
+    extern __shared__ __align__(16) double pigs_smem_base[];
+    const int ntab = cP.Nmax + 2;
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) { pigs_smem_base[i] = cP.vtab[i]; pigs_smem_base[ntab + i] = cP.logwf[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned h = warp * 2654435761u + 12345u;
+    double acc = 0.0;
+    const size_t ss = (size_t)3 * cP.NpS;
+    Partner first; first.x = first.y = first.z = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        h = h * 1664525u + 1013904223u;
+#ifdef CALLS
+        h = other_work(h, out);
+#endif
+        int s = (h >> 8) % nslices;
+        const double* Rx = slices + (size_t)s * ss;
+        int ip0 = (h >> 3) % cP.Np;
+        int ib = KINDSEL == 0 ? 2 : (KINDSEL == 1 ? 3 : (KINDSEL == 2 ? 0 : 1 + (int)((h >> 20) % 29)));
+        double xo[3] = {Rx[ip0], Rx[cP.NpS + ip0], Rx[2 * cP.NpS + ip0]};
+        double xn[3] = {xo[0] + 0.05, xo[1] - 0.03, xo[2] + 0.02};
+        if (lane < cP.Np) first = load_partner(Rx, lane);
+#ifdef NOINL
+        acc += wrapped(Rx, ip0, ib, lane, xo, xn, first);
+#else
+        acc += bead_eval<false, true, true, false>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn, lane, nullptr, first);
+#endif
+    }
+    if (lane == 0) out[warp] = acc;
+}
+
+int main(int argc, char** argv) {
+    int Np = argc > 1 ? atoi(argv[1]) : 256;
+    int nslices = argc > 2 ? atoi(argv[2]) : 65536;
+    int iters = argc > 3 ? atoi(argv[3]) : 2000;
+    int warps_per_sm = argc > 4 ? atoi(argv[4]) : 16;
+    DevParams P; memset(&P, 0, sizeof P);
+    P.dim = 3; P.Np = Np; P.Nb = 15; P.S = 31; P.NpS = (Np + 3) & ~3; P.Nmax = 10000;
+    double L = cbrt(Np / 0.365);
+    for (int k = 0; k < 3; ++k) { P.L[k] = L; P.Lh[k] = L / 2; P.invL[k] = 1 / L; }
+    double rcut = L / 2; P.rcut2 = rcut * rcut; P.dr = rcut / 9999.0; P.inv_dr = 1 / P.dr; P.dt = 5e-3;
+    std::vector<double> tab(10002), slices((size_t)nslices * 3 * P.NpS);
+    for (int i = 0; i < 10002; ++i) { double r = (i + 1) * P.dr; tab[i] = 1.0 / (r * r * r + 0.1); }
+    for (auto& v : slices) v = (rand() / (double)RAND_MAX - 0.5) * L;
+    double *d_tab, *d_sl, *d_out;
+    cudaMalloc(&d_tab, tab.size() * 8); cudaMalloc(&d_sl, slices.size() * 8); cudaMalloc(&d_out, 1 << 22);
+    cudaMemcpy(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_sl, slices.data(), slices.size() * 8, cudaMemcpyHostToDevice);
+    P.vtab = d_tab; P.logwf = d_tab;
+    cudaMemcpyToSymbol(cP, &P, sizeof P);
+    size_t smem = 2 * 10002 * 8;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    auto run = [&](auto kern, const char* name) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int block = warps_per_sm * 32, grid = 148;
+        kern<<<grid, block, smem>>>(d_sl, nslices, 10, d_out);
+        cudaEventRecord(a); kern<<<grid, block, smem>>>(d_sl, nslices, iters, d_out); cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        double upd = (double)grid * warps_per_sm * iters;
+        printf("%-6s Np=%d slices=%d (%.0f MB) warps/SM=%d: %.1f M bead-updates/s  (%s)\n", name, Np, nslices, slices.size() * 8 / 1e6, warps_per_sm, upd / ms / 1e3, cudaGetErrorString(cudaGetLastError()));
+    };
+    run(k_loop<0>, "even"); run(k_loop<1>, "odd"); run(k_loop<2>, "end"); run(k_loop<3>, "mixed");
+    return 0;
+}
