@@ -171,7 +171,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     DevParams& P = h->P;
     std::memset(&P, 0, sizeof P);
     P.dim = p->dim; P.Np = p->Np; P.Nb = p->Nb; P.S = 2 * p->Nb + 1;
-    P.NpS = (p->Np + 3) & ~3;                 // 32-byte aligned component rows
+    P.NpS = (p->Np + 31) & ~31;               // whole [3][32] blocks (pidx, pigs_device.cuh)
     P.Nmax = p->Nmax; P.Nbin = p->Nbin; P.Nk = p->Nk; P.Npw = p->Npw;
     P.trap = p->trap != 0; P.sampling = p->sampling; P.Lstag = p->Lstag; P.Nlev = p->Nlev; P.Nstag = p->Nstag;
     P.Nobdm = p->Nobdm; P.swapping = p->swapping != 0; P.CMFreq = p->CMFreq; P.n_chains = p->n_chains;
@@ -536,12 +536,12 @@ extern "C" int pigs_move(pigs_handle h, int move, int ip, int half, int32_t* acc
     return PIGS_OK;
 }
 
-// host AoS [n][Np][dim] -> device SoA [n][3][NpS] (unit calls are test-sized; transposed on the host)
+// host AoS [n][Np][dim] -> device blocked SoA [n][NpS/32][3][32] (unit calls are test-sized; transposed on the host)
 static void to_soa(const DevParams& P, long long nslice, const double* aos, std::vector<double>& soa) {
     soa.assign((size_t)nslice * 3 * P.NpS, 0.0);
     for (long long s = 0; s < nslice; ++s)
         for (int ip = 0; ip < P.Np; ++ip)
-            for (int k = 0; k < P.dim; ++k) soa[((size_t)s * 3 + k) * P.NpS + ip] = aos[((size_t)s * P.Np + ip) * P.dim + k];
+            for (int k = 0; k < P.dim; ++k) soa[(size_t)s * 3 * P.NpS + pidx(ip) + 32 * k] = aos[((size_t)s * P.Np + ip) * P.dim + k];
 }
 struct DevBuf {
     void* p = nullptr;

@@ -68,7 +68,7 @@ struct DevParams {
     unsigned long long seed;
     const double* logwf;      // (0:Nmax+1) in global memory
     const double* vtab;
-    double* path;             // [chain][ib][k][NpS]
+    double* path;             // [chain][ib][NpS/32][k][32]  (see pidx)
     double* xend;             // [chain][2][3]
     int* istate;              // [chain][IS_N]
     int* cyc;                 // [chain][Np]  Particles_in_perm_cycle
@@ -162,8 +162,15 @@ __device__ __forceinline__ double* part_of(GS* gs) { return seg_old(gs) + 6 * cP
 __device__ __forceinline__ double* pp_of(GS* gs) { return part_of(gs) + part_slots(cA.threads_per_chain >> 5) * 8; }
 __device__ __forceinline__ double& so(GS* gs, int k, int ib) { return seg_old(gs)[k * cP.S + ib]; }
 __device__ __forceinline__ double& sn(GS* gs, int k, int ib) { return seg_new(gs)[k * cP.S + ib]; }
+// A time slice is stored as NpS/32 blocks of [3][32] doubles: x, y, z of 32
+// consecutive particles side by side (768 contiguous bytes).  A warp of the
+// partner loop reads one block per iteration: one pointer, immediate offsets
+// for y and z, and one DRAM burst instead of three pieces 8*NpS bytes apart.
+// NpS = Np rounded up to 32; the padding of the last block is zero and never read.
+constexpr int PY = 32, PZ = 64, PBLK = 96;
+__host__ __device__ __forceinline__ int pidx(int j) { return (j >> 5) * PBLK + (j & 31); }
 __device__ __forceinline__ double* slice(GS* gs, int ib) { return gs->path + (size_t)ib * 3 * cP.NpS; }
-__device__ __forceinline__ double& pth(GS* gs, int k, int ip0, int ib) { return gs->path[((size_t)ib * 3 + k) * cP.NpS + ip0]; }
+__device__ __forceinline__ double& pth(GS* gs, int k, int ip0, int ib) { return gs->path[(size_t)ib * 3 * cP.NpS + pidx(ip0) + 32 * k]; }
 
 // ------------------------------------------------------------------ tables
 // VAR 0: both tables through the read-only L1/L2 path; 1: VTable in shared
@@ -516,7 +523,8 @@ struct Partner {
 };
 __device__ __forceinline__ Partner load_partner(const double* Rx, int j) {
     Partner p;
-    p.x = ldpath(Rx + j); p.y = ldpath(Rx + cP.NpS + j); p.z = ldpath(Rx + 2 * cP.NpS + j);
+    const double* q = Rx + pidx(j);
+    p.x = ldpath(q); p.y = ldpath(q + PY); p.z = ldpath(q + PZ);
     return p;
 }
 
@@ -580,18 +588,15 @@ __device__ __forceinline__ void pair_loop(int kind, const double* Rx, int ip0, i
                                           const double (&xn)[3], Partner nxt, double& pot, double& psi, double (&fn)[3],
                                           double (&fo)[3]) {
     // running pointer + countdown: no per-iteration address arithmetic, no loop-invariant reloads
-    const double* p = Rx + j0;
-    const long long sy = cP.NpS;
+    // (j0 = 32*s + lane and jstride = 32*split: the warp walks whole [3][32] blocks)
+    const double* p = Rx + pidx(j0);
+    const int pstep = 3 * jstride;
     const int self_left = cP.Np - ip0;
 PIGS_PRAGMA_UNROLL
     for (int left = cP.Np - j0; left > 0; left -= jstride) {
         const Partner cur = nxt;
-        p += jstride;
-#ifdef PIGS_BLOCKED_TEST
-        if (left > jstride) { const double* pb = Rx + 96 * ((p - Rx) >> 5) + ((p - Rx) & 31); nxt.x = ldpath(pb); nxt.y = ldpath(pb + 32); nxt.z = ldpath(pb + 64); }
-#else
-        if (left > jstride) { nxt.x = ldpath(p); nxt.y = ldpath(p + sy); nxt.z = ldpath(p + 2 * sy); }
-#endif
+        p += pstep;
+        if (left > jstride) { nxt.x = ldpath(p); nxt.y = ldpath(p + PY); nxt.z = ldpath(p + PZ); }
         pair_body<TRAP, VSM, WSM, VPAIR>(kind, left != self_left, cur, xo, xn, pot, psi, fn, fo);
     }
 }

@@ -18,7 +18,7 @@ cudaError_t sweep_max_threads(int mt, int var, int* n);      // the instantiatio
 enum UnitOp { U_LOCAL_ENERGY = 0, U_THERM_ENERGY = 1, U_PAIR_CORR = 2, U_SOFK = 3, U_OBDM = 4 };
 struct UnitArgs {
     int op, n;
-    const double* in;    // SoA slices [n][3][NpS] / paths [n][S][3][NpS] / xend [n][2][3]
+    const double* in;    // blocked SoA slices [n][NpS/32][3][32] / paths [n][S][NpS/32][3][32] / xend [n][2][3]
     double* out;         // [n][3] energies / histograms [n][...]
 };
 cudaError_t launch_unit(bool trap, const DevParams& P, const UnitArgs& A, cudaStream_t st);

@@ -685,14 +685,14 @@ __device__ __forceinline__ void group_sum(GS* gs, double (&v)[N]) {
 template <int VAR>
 static __device__ __noinline__ void LocalEnergy(GS* gs, const double* Rx, double* out) {
     const Grp G = grp();
-    const double* Ry = Rx + cP.NpS;
-    const double* Rz = Ry + cP.NpS;
+    const double* Ry = Rx + PY;
+    const double* Rz = Rx + PZ;
     const double* tV = gs->tabV;
     const double* tW = gs->tabW;
     double s[4] = {0.0, 0.0, 0.0, 0.0};      // sum |F_i|^2, pair lap (x2), pair pot (x2), one-body pot
     double oneLap = 0.0;
     for (int i = G.tid; i < cP.Np; i += G.size) {
-        double xi[3] = {Rx[i], Ry[i], Rz[i]};
+        double xi[3] = {Rx[pidx(i)], Ry[pidx(i)], Rz[pidx(i)]};
         double F[3] = {0.0, 0.0, 0.0}, lap = 0.0, pot = 0.0;
         if (PIGS_TRAP) {
 #pragma unroll
@@ -705,7 +705,7 @@ static __device__ __noinline__ void LocalEnergy(GS* gs, const double* Rx, double
         }
         for (int j = 0; j < cP.Np; ++j) {
             if (j == i) continue;
-            double d0 = xi[0] - Rx[j], d1 = xi[1] - Ry[j], d2 = xi[2] - Rz[j];
+            double d0 = xi[0] - Rx[pidx(j)], d1 = xi[1] - Ry[pidx(j)], d2 = xi[2] - Rz[pidx(j)];
             if (!PIGS_TRAP) {
                 d0 = mimg(d0, cP.L[0], cP.Lh[0]); d1 = mimg(d1, cP.L[1], cP.Lh[1]); d2 = mimg(d2, cP.L[2], cP.Lh[2]);
             }
@@ -749,10 +749,10 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
     for (int it = G.tid; it < nitem; it += G.size) {
         int ib = it / cP.Np, i = it - ib * cP.Np;
         const double* Rx = slice(gs, ib);
-        const double* Ry = Rx + cP.NpS;
-        const double* Rz = Ry + cP.NpS;
+        const double* Ry = Rx + PY;
+        const double* Rz = Rx + PZ;
         const bool odd = (ib & 1) && !cP.primitive;        // slices that need the force term
-        double xi[3] = {Rx[i], Ry[i], Rz[i]};
+        double xi[3] = {Rx[pidx(i)], Ry[pidx(i)], Rz[pidx(i)]};
         double F[3] = {0.0, 0.0, 0.0}, pot = 0.0, one = 0.0;
         if (PIGS_TRAP) {
 #pragma unroll
@@ -766,7 +766,7 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
             // forces are needed for every particle: particle i sums over all j (each pair is seen twice)
             for (int j = 0; j < cP.Np; ++j) {
                 if (j == i) continue;
-                double d0 = xi[0] - Rx[j], d1 = xi[1] - Ry[j], d2 = xi[2] - Rz[j];
+                double d0 = xi[0] - Rx[pidx(j)], d1 = xi[1] - Ry[pidx(j)], d2 = xi[2] - Rz[pidx(j)];
                 if (!PIGS_TRAP) {
                     d0 = mimg_fast(d0, cP.L[0], cP.invL[0]); d1 = mimg_fast(d1, cP.L[1], cP.invL[1]); d2 = mimg_fast(d2, cP.L[2], cP.invL[2]);
                 }
@@ -791,7 +791,7 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
             for (int m = 1; m <= half; ++m) {
                 if (!(cP.Np & 1) && m == half && i >= half) break;
                 int j = i + m; if (j >= cP.Np) j -= cP.Np;
-                double d0 = xi[0] - Rx[j], d1 = xi[1] - Ry[j], d2 = xi[2] - Rz[j];
+                double d0 = xi[0] - Rx[pidx(j)], d1 = xi[1] - Ry[pidx(j)], d2 = xi[2] - Rz[pidx(j)];
                 if (!PIGS_TRAP) {
                     d0 = mimg_fast(d0, cP.L[0], cP.invL[0]); d1 = mimg_fast(d1, cP.L[1], cP.invL[1]); d2 = mimg_fast(d2, cP.L[2], cP.invL[2]);
                 }
@@ -811,7 +811,7 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
         if (ib == cP.Nb) s[1] += potsh;
         // kinetic link ib -> ib+1 (sample_mod.f90:359-380)
         const double* Nx = slice(gs, ib + 1);
-        double l0 = xi[0] - Nx[i], l1 = xi[1] - Nx[cP.NpS + i], l2 = xi[2] - Nx[2 * cP.NpS + i];
+        double l0 = xi[0] - Nx[pidx(i)], l1 = xi[1] - Nx[pidx(i) + PY], l2 = xi[2] - Nx[pidx(i) + PZ];
         if (!PIGS_TRAP) {
             l0 = mimg(l0, cP.L[0], cP.Lh[0]); l1 = mimg(l1, cP.L[1], cP.Lh[1]); l2 = mimg(l2, cP.L[2], cP.Lh[2]);
         }
@@ -828,17 +828,17 @@ static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
 // small integers, so atomic accumulation in any order is exact.
 static __device__ __noinline__ void PairCorrelation(const double* Rx, double* gr) {
     const Grp G = grp();
-    const double* Ry = Rx + cP.NpS;
-    const double* Rz = Ry + cP.NpS;
+    const double* Ry = Rx + PY;
+    const double* Rz = Rx + PZ;
     const int Np = cP.Np, half = Np / 2;
     // pair (i, (i+m) mod Np), m = 1..half; for even Np the m == half pairs are taken from i < half only
     for (int it = G.tid; it < Np * half; it += G.size) {
         int i = it / half, m = it - i * half + 1;
         if (!(Np & 1) && m == half && i >= half) continue;
         int j = i + m; if (j >= Np) j -= Np;
-        double d0 = mimg(Rx[i] - Rx[j], cP.L[0], cP.Lh[0]);
-        double d1 = mimg(Ry[i] - Ry[j], cP.L[1], cP.Lh[1]);
-        double d2 = mimg(Rz[i] - Rz[j], cP.L[2], cP.Lh[2]);
+        double d0 = mimg(Rx[pidx(i)] - Rx[pidx(j)], cP.L[0], cP.Lh[0]);
+        double d1 = mimg(Ry[pidx(i)] - Ry[pidx(j)], cP.L[1], cP.Lh[1]);
+        double d2 = mimg(Rz[pidx(i)] - Rz[pidx(j)], cP.L[2], cP.Lh[2]);
         // no FMA contraction: keeps the bin index bit-identical to the reference's arithmetic
         double r2 = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
         if (r2 <= cP.rcut2) {
@@ -852,11 +852,11 @@ static __device__ __noinline__ void StructureFactor(const double* Rx, double* Sk
     const Grp G = grp();
     for (int it = G.tid; it < cP.Nk * cP.dim; it += G.size) {
         int iq = it / cP.dim + 1, k = it - (iq - 1) * cP.dim;
-        const double* X = Rx + k * cP.NpS;
+        const double* X = Rx + 32 * k;
         double q = (double)iq * cP.qbin[k], sc = 0.0, ss = 0.0;
         for (int ip = 0; ip < cP.Np; ++ip) {
             double s, c;
-            sincos(q * X[ip], &s, &c);
+            sincos(q * X[pidx(ip)], &s, &c);
             sc += c; ss += s;
         }
         Sk[it] += sc * sc + ss * ss;          // Sk(k,iq) column-major == [iq][k]

@@ -112,12 +112,12 @@ cudaError_t launch_update_action(bool trap, const DevParams& P, int n, const dou
 }
 
 // ---------------------------------------------------------------- layout transposes
-// aos: [chain][ib][ip][dim]  <->  soa: [chain][ib][3][NpS]
+// aos: [chain][ib][ip][dim]  <->  blocked soa: [chain][ib][NpS/32][3][32]  (pidx, pigs_device.cuh)
 __global__ void k_aos_to_soa(const __grid_constant__ DevParams P, const double* aos, double* soa, long long nslice) {
     const long long per = (long long)3 * P.NpS;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nslice * per; i += (long long)gridDim.x * blockDim.x) {
         long long s = i / per;
-        int r = (int)(i - s * per), k = r / P.NpS, ip = r - k * P.NpS;
+        int r = (int)(i - s * per), blk = r / PBLK, w = r - blk * PBLK, k = w >> 5, ip = blk * 32 + (w & 31);
         double v = 0.0;
         if (k < P.dim && ip < P.Np) v = aos[(s * P.Np + ip) * P.dim + k];
         soa[i] = v;
@@ -128,7 +128,7 @@ __global__ void k_soa_to_aos(const __grid_constant__ DevParams P, const double* 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nslice * per; i += (long long)gridDim.x * blockDim.x) {
         long long s = i / per;
         int r = (int)(i - s * per), ip = r / P.dim, k = r - ip * P.dim;
-        aos[i] = soa[(s * 3 + k) * P.NpS + ip];
+        aos[i] = soa[s * 3 * P.NpS + pidx(ip) + 32 * k];
     }
 }
 cudaError_t launch_aos_to_soa(const DevParams& P, const double* aos, double* soa, int nchain, cudaStream_t st) {

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(512, 1) k_loop(const double* slices, int nslic
         const double* Rx = slices + (size_t)s * ss;
         int ip0 = (h >> 3) % cP.Np;
         int ib = KINDSEL == 0 ? 2 : (KINDSEL == 1 ? 3 : (KINDSEL == 2 ? 0 : 1 + (int)((h >> 20) % 29)));
-        double xo[3] = {Rx[ip0], Rx[cP.NpS + ip0], Rx[2 * cP.NpS + ip0]};
+        double xo[3] = {Rx[pidx(ip0)], Rx[pidx(ip0) + PY], Rx[pidx(ip0) + PZ]};
         double xn[3] = {xo[0] + 0.05, xo[1] - 0.03, xo[2] + 0.02};
         if (lane < cP.Np) first = load_partner(Rx, lane);
         acc += bead_eval<false, true, true, false>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn, lane, nullptr, first);
@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
     int iters = argc > 3 ? atoi(argv[3]) : 2000;
     int warps_per_sm = argc > 4 ? atoi(argv[4]) : 16;
     DevParams P; memset(&P, 0, sizeof P);
-    P.dim = 3; P.Np = Np; P.Nb = 15; P.S = 31; P.NpS = (Np + 3) & ~3; P.Nmax = 10000;
+    P.dim = 3; P.Np = Np; P.Nb = 15; P.S = 31; P.NpS = (Np + 31) & ~31; P.Nmax = 10000;
     double L = cbrt(Np / 0.365);
     for (int k = 0; k < 3; ++k) { P.L[k] = L; P.Lh[k] = L / 2; P.invL[k] = 1 / L; }
     double rcut = L / 2; P.rcut2 = rcut * rcut; P.dr = rcut / 9999.0; P.inv_dr = 1 / P.dr; P.dt = 5e-3;
