@@ -65,6 +65,7 @@ struct DevParams {
     //   sig_bis[l]   = sqrt(0.5*(0.5*real(2**l)*dt))           bisection, delta_ib = 2**l     (vpi_mod.f90:906-907)
     double sig_free[MAXS], sig_stage[MAXS], sig_bis[16];
     double half_inv_dt2;
+    double half_inv_dr2;      // 0.5/dr^2 (centred difference of the table)
     unsigned long long seed;
     const double* logwf;      // (0:Nmax+1) in global memory
     const double* vtab;
@@ -245,7 +246,7 @@ __device__ __forceinline__ void lk_val_d1_pair(const Lk& k, double& v, double& d
     double Fb = k.a1 * lo.y + k.a2 * lo.x;
     double Fa = k.a1 * hi.y + k.a2 * hi.x;
     v = Fc * cP.inv_dr;
-    d1 = (Fa - Fb) * (0.5 * cP.inv_dr * cP.inv_dr);
+    d1 = (Fa - Fb) * cP.half_inv_dr2;
 }
 template <bool SM, int WHICH, bool VF>
 __device__ __forceinline__ double lk_val(const Lk& k) {   // opt 0
@@ -258,7 +259,7 @@ __device__ __forceinline__ void lk_val_d1(const Lk& k, double& v, double& d1) { 
     double Fb = k.a1 * f0 + k.a2 * fm;
     double Fa = k.a1 * f2 + k.a2 * f1;
     v = Fc * cP.inv_dr;
-    d1 = (Fa - Fb) * (0.5 * cP.inv_dr * cP.inv_dr);
+    d1 = (Fa - Fb) * cP.half_inv_dr2;
 }
 
 // Interpolate opt 0, 1 and 2 in the reference's exact operation order, true
