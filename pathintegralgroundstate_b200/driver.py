@@ -43,6 +43,15 @@ def fortran_f(x: float, w: int, d: int) -> str:
     return s.rjust(w) if len(s) <= w else "*" * w
 
 
+def _scaled(a: float, ex: int) -> float:
+    """a / 10**ex without overflow or underflow of the power at the ends of the double range"""
+    if ex > 300:
+        return a / 1e300 / 10.0 ** (ex - 300)
+    if ex < -300:
+        return a * 1e300 / 10.0 ** (ex + 300)
+    return a / 10.0 ** ex
+
+
 def fortran_e(x: float, w: int, d: int, e: int) -> str:
     """Ew.dEe with the default scale factor 0: 0.dddddE+eee"""
     if x == 0.0 or not math.isfinite(x):
@@ -56,11 +65,10 @@ def fortran_e(x: float, w: int, d: int, e: int) -> str:
         sgn = "-" if x < 0 else ""
         a = abs(x)
         ex = int(math.floor(math.log10(a))) + 1
-        m = a / 10.0 ** ex
-        ms = f"{m:.{d}f}"
+        ms = f"{_scaled(a, ex):.{d}f}"
         if ms.startswith("1."):            # rounding carried into the next decade
             ex += 1
-            ms = f"{a / 10.0 ** ex:.{d}f}"
+            ms = f"{_scaled(a, ex):.{d}f}"
         mant = ms
     s = f"{sgn}{mant}E{'+' if ex >= 0 else '-'}{abs(ex):0{e}d}"
     if len(s) > w and s.lstrip("-").startswith("0."):
@@ -364,6 +372,9 @@ def main(argv=None):
     ap.add_argument("--potential", default="hfdb", choices=["hfdb", "hfdhe2", "zero"])
     a = ap.parse_args(argv)
     cfg = read_vpi_in(sys.stdin.read())
+    if cfg.get("crystal"):                       # Np, Lbox, density come from config_ini.in (vpi.f90:101-107)
+        from .host import read_config_ini
+        cfg["Np"], cfg["Lbox"], cfg["density"], _ = read_config_ini(os.path.join(a.workdir, "config_ini.in"), int(cfg["dim"]))
     cu = cfg.get("cuda", {})
     n = a.chains or int(cu.get("n_chains", 1))
     rng = a.rng or str(cu.get("rng", "mt" if n == 1 else "philox"))

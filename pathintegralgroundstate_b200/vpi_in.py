@@ -108,3 +108,37 @@ def read_vpi_in(text: str) -> dict:
         cfg["sampling"] = cfg["sampling"].strip()[:3]
     cfg["cuda"] = dict(nl.get("cuda", {}))
     return cfg
+
+
+def format_vpi_in(cfg: dict, cuda: dict | None = None) -> str:
+    """The inverse of read_vpi_in: a vpi.in for the reference (and, with the optional
+    &cuda group, for vpi_cuda / this package's driver) from a flat configuration."""
+    def lit(v):
+        if isinstance(v, bool):
+            return "T" if v else "F"
+        if isinstance(v, int):
+            return str(v)
+        if isinstance(v, float):
+            return repr(v).replace("e", "d") if "e" in repr(v) else repr(v) + "d0"
+        if isinstance(v, (list, tuple)):
+            return ", ".join(lit(x) for x in v)
+        return "'" + str(v) + "'"
+    full = dict(DEFAULTS)
+    full.update(cfg)
+    out = []
+    for g in ("system", "samp", "obdm", "wavefun", "jastrow", "extpot"):
+        if g == "extpot" and not full.get("trap"):
+            continue
+        out.append("&" + g)
+        for name in GROUPS[g]:
+            if name in full:
+                out.append(f" {name} = {lit(full[name])},")
+        out.append("/")
+    cu = dict(cuda or cfg.get("cuda") or {})
+    if cu:
+        out.append("&cuda")
+        for name in GROUPS["cuda"]:
+            if name in cu:
+                out.append(f" {name} = {lit(cu[name])},")
+        out.append("/")
+    return "\n".join(out) + "\n"

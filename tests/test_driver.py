@@ -2,14 +2,28 @@
 descriptors, checkpoint/rand_state formats, and the whole driver run over the
 CPU oracle (CPU test) and over libpigs_cuda (GPU test) with the files compared."""
 import os
+import subprocess
 
 import numpy as np
 import pytest
 
 from pathintegralgroundstate_b200.driver import (fortran_g, fortran_e, fortran_f, g_line, var, write_checkpoint,
                                                  read_checkpoint, append_rand_state, read_rand_state, VpiDriver)
+from pathintegralgroundstate_b200.vpi_in import format_vpi_in, read_vpi_in
+from pathintegralgroundstate_b200 import derive_geometry
 from tests.common import C1, CWX, CW
 from tests.oracle_backend import OracleBackend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VPI = os.path.join(ROOT, "pathintegralgroundstate_b200", "vpi_cuda")
+
+
+def _vpi(args, stdin, cwd=None):
+    """run the compiled driver (csrc/vpi_main.cpp, built by csrc/Makefile / __graft_entry__.build)"""
+    assert os.path.exists(VPI), f"{VPI} is missing: make -C pathintegralgroundstate_b200/csrc"
+    r = subprocess.run([VPI] + list(args), input=stdin, capture_output=True, text=True, cwd=cwd, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
 
 
 def test_fortran_g_editing():
@@ -104,3 +118,77 @@ def test_driver_gpu_replay_matches_driver_over_oracle(tmp_path, cfgname):
     # integer files are identical byte for byte; the random state record too
     assert open(a / "fort.99").read() == open(b / "fort.99").read()
     assert open(a / "rand_state", "rb").read() == open(b / "rand_state", "rb").read()
+
+
+# ------------------------------------------------------------------ the compiled driver (vpi_cuda)
+def test_vpi_cuda_g_editing_matches_python():
+    rng = np.random.default_rng(7)
+    xs = [0.0, -0.0, 1.0, 0.1, 0.09999999999, 0.099999999995, 9999999999.4, 9999999999.5, 1e10, 123.456, -3.4187286, 1e-5, -2.5e12,
+          1e-310, 1.7976931348623157e308, 5e-324, 0.99999999995, 9.9999999995, 99999.999995, float("nan"), float("inf"), -float("inf")]
+    xs += list(rng.normal(size=400) * 10.0 ** rng.integers(-12, 13, size=400))
+    xs += [float(f"{m}e{e}") for m in ("9.99999999949", "9.9999999995", "9.99999999951", "1", "4.5", "-9.9999999995") for e in range(-4, 12)]
+    cases = [(20, 10, 3, x) for x in xs] + [(16, 8, 2, x) for x in xs[:200]]
+    out = _vpi(["--format-test"], "".join(f"{w} {d} {e} {float(x)!r}\n" for w, d, e, x in cases)).split("\n")[:-1]
+    assert len(out) == len(cases)
+    for (w, d, e, x), got in zip(cases, out):
+        assert got == fortran_g(x, w, d, e), (x, got, fortran_g(x, w, d, e))
+
+
+@pytest.mark.parametrize("cfgname", ["CWX", "C1"])
+def test_vpi_cuda_reads_vpi_in_and_writes_the_tables(tmp_path, cfgname):
+    cfg = dict(dict(CWX=CWX, C1=C1)[cfgname], Nblock=3, Nstep=8)
+    pot = "zero" if cfgname == "C1" else "hfdb"
+    text = "! a comment line\n" + format_vpi_in(cfg, cuda=dict(n_chains=7, rng="mt"))
+    assert read_vpi_in(text)["cuda"] == dict(n_chains=7, rng="mt")
+    a, b = tmp_path / "cxx", tmp_path / "py"
+    out = _vpi(["--tables-only", "--workdir", str(a), "--potential", pot], text)
+    kv = {ln.split()[0]: ln.split()[1:] for ln in out.splitlines()[1:]}
+    g = derive_geometry(cfg)
+    head = out.splitlines()[0].split()
+    assert head[1::2][:4] == [str(cfg["dim"]), str(cfg["Np"]), str(cfg["Nb"]), "10000"] and head[9] == cfg["sampling"] and head[11] == "7"
+    for k in ("rcut", "dr", "rbin", "density", "delta_cm"):
+        assert float(kv[k][0]) == g[k], k                      # %.17g round-trips: identical doubles
+    assert [float(t) for t in kv["Lbox"]] == list(g["Lbox"])
+    VpiDriver(cfg, OracleBackend(cfg), workdir=str(b), potential=pot, quiet=True).tables()
+    for f in ("jastrow.out", "potential.out"):
+        assert open(a / f).read() == open(b / f).read(), f
+
+
+def _compare_run_dirs(a, b, files):
+    for f in files:
+        assert os.path.exists(a / f) == os.path.exists(b / f), f
+        if os.path.exists(a / f):
+            assert open(a / f, "rb").read() == open(b / f, "rb").read(), f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfgname", ["CWX", "C1", "CS"])
+def test_vpi_cuda_matches_python_driver_byte_for_byte(tmp_path, cfgname):
+    """the compiled program and the Python driver are the same program over the same C ABI: every file identical"""
+    from pathintegralgroundstate_b200 import PigsCuda
+    from tests.common import CS
+    cfg = dict(dict(CWX=CWX, C1=C1, CS=CS)[cfgname], Nblock=3, Nstep=8)
+    pot = "zero" if cfgname == "C1" else "hfdb"
+    a, b = tmp_path / "cxx", tmp_path / "py"
+    out = _vpi(["--workdir", str(a), "--potential", pot], format_vpi_in(cfg, cuda=dict(n_chains=1, rng="mt")))
+    d = VpiDriver(cfg, PigsCuda(cfg, n_chains=1, rng="mt", seed=cfg["seed"]), workdir=str(b), potential=pot, quiet=True)
+    d.run()
+    files = ["e_vpi.out", "et_vpi.out", "gr_vpi.out", "sk_vpi.out", "nr_vpi.out", "fort.99", "checkpoint.dat", "rand_state",
+             "jastrow.out", "potential.out"]
+    _compare_run_dirs(a, b, files)
+    strip = lambda lines: [ln for ln in lines if not ln.startswith(" # Time per block")]
+    assert strip(out.splitlines()) == strip(d.out)
+    # resume from the files the compiled program wrote (vpi_mod.f90:162-185): both continue identically
+    cfg2 = dict(cfg, resume=True, Nblock=2)
+    _vpi(["--workdir", str(a), "--potential", pot], format_vpi_in(cfg2, cuda=dict(n_chains=1, rng="mt")))
+    VpiDriver(cfg2, PigsCuda(cfg2, n_chains=1, rng="mt", seed=cfg["seed"]), workdir=str(b), potential=pot, quiet=True).run()
+    _compare_run_dirs(a, b, ["e_vpi.out", "et_vpi.out", "checkpoint.dat", "fort.99"])
+
+
+@pytest.mark.gpu
+def test_vpi_cuda_many_chains_philox(tmp_path):
+    cfg = dict(CWX, Nblock=2, Nstep=6)
+    out = _vpi(["--workdir", str(tmp_path)], format_vpi_in(cfg, cuda=dict(n_chains=64, rng="philox")))
+    assert "Markov chains (GPU) :    64" in out and "FINAL RESULTS" in out
+    e = np.loadtxt(tmp_path / "e_vpi.out")
+    assert e.shape == (2, 4) and np.all(np.isfinite(e))
