@@ -86,8 +86,8 @@ static int plan(pigs_ctx* h) {
     }
     if (T != 32 && T != 64 && T != 128 && T != 256 && T != 512) return fail(PIGS_E_ARG, "threads_per_chain must be 0,32,64,128,256,512");
     const size_t gbytes = (grp_smem_bytes(h->P.S, h->P.Np, T / 32) + 15) & ~(size_t)15;
-    const size_t tabbytes = (size_t)(p.Nmax + 2) * sizeof(double);
-    const size_t pairbytes = (size_t)(p.Nmax + 1) * 2 * sizeof(double);      // table_mode 1: {F(i),F(i+1)} pairs
+    const size_t tabbytes = (size_t)tab_len(p.Nmax) * sizeof(double);
+    const size_t pairbytes = (size_t)(tab_len(p.Nmax) - 1) * 2 * sizeof(double);      // table_mode 1: {F(i),F(i+1)} pairs
     int maxt = 1024;
     CK(sweep_max_threads(h->mt, p.trap ? 3 : 0, &maxt));
     if (T > maxt) return fail(PIGS_E_ARG, "threads_per_chain exceeds the kernel's launch bound");
@@ -185,6 +185,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     }
     P.rcut2 = p->rcut * p->rcut;              // vpi.f90:127
     P.dr = p->dr; P.inv_dr = 1.0 / p->dr; P.half_inv_dr2 = 0.5 * P.inv_dr * P.inv_dr;
+    P.rclamp2 = ((double)p->Nmax + 3.5) * p->dr * ((double)p->Nmax + 3.5) * p->dr;
     P.rbin = p->rcut / (double)(float)p->Nbin;   // vpi.f90:128
     P.dt = p->dt; P.delta_cm = p->delta_cm; P.CWorm = p->CWorm; P.density = p->density;
     P.pi = std::acos(-1.0);
@@ -213,7 +214,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
 
     const size_t nc = (size_t)p->n_chains;
 #define ALLOC(ptr, count) CK(cudaMalloc((void**)&(ptr), sizeof(*(ptr)) * (count)))
-    ALLOC(h->d_logwf, p->Nmax + 2); ALLOC(h->d_vtab, p->Nmax + 2);
+    ALLOC(h->d_logwf, tab_len(p->Nmax)); ALLOC(h->d_vtab, tab_len(p->Nmax));      // zero tail: TAB_PAD
     ALLOC(h->d_path, nc * P.chain_stride); ALLOC(h->d_xend, nc * 6);
     ALLOC(h->d_istate, nc * IS_N); ALLOC(h->d_cyc, nc * P.Np); ALLOC(h->d_hist, nc * P.Np);
     ALLOC(h->d_mt, nc * 624); ALLOC(h->d_pctr, nc); ALLOC(h->d_acc, nc * P.nacc); ALLOC(h->d_cnt, nc * NCNT);
@@ -227,8 +228,8 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     CK(cudaMemset(h->d_pctr, 0, sizeof(unsigned long long) * nc));
     CK(cudaMemset(h->d_acc, 0, sizeof(double) * nc * P.nacc));
     CK(cudaMemset(h->d_cnt, 0, sizeof(long long) * nc * NCNT));
-    CK(cudaMemset(h->d_logwf, 0, sizeof(double) * (p->Nmax + 2)));
-    CK(cudaMemset(h->d_vtab, 0, sizeof(double) * (p->Nmax + 2)));
+    CK(cudaMemset(h->d_logwf, 0, sizeof(double) * tab_len(p->Nmax)));
+    CK(cudaMemset(h->d_vtab, 0, sizeof(double) * tab_len(p->Nmax)));
     P.logwf = h->d_logwf; P.vtab = h->d_vtab; P.path = h->d_path; P.xend = h->d_xend; P.istate = h->d_istate;
     P.cyc = h->d_cyc; P.hist = h->d_hist; P.mt = h->d_mt; P.pctr = h->d_pctr; P.acc = h->d_acc; P.cnt = h->d_cnt;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));

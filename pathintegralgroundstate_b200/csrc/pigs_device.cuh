@@ -66,6 +66,7 @@ struct DevParams {
     double sig_free[MAXS], sig_stage[MAXS], sig_bis[16];
     double half_inv_dt2;
     double half_inv_dr2;      // 0.5/dr^2 (centred difference of the table)
+    double rclamp2;           // ((Nmax+3.5)*dr)^2: where masked pairs are looked up (zero tail of the tables)
     unsigned long long seed;
     const double* logwf;      // (0:Nmax+1) in global memory
     const double* vtab;
@@ -169,6 +170,11 @@ __device__ __forceinline__ double& sn(GS* gs, int k, int ib) { return seg_new(gs
 // for y and z, and one DRAM burst instead of three pieces 8*NpS bytes apart.
 // NpS = Np rounded up to 32; the padding of the last block is zero and never read.
 constexpr int PY = 32, PZ = 64, PBLK = 96;
+// Device tables carry TAB_PAD zero entries behind the reference's F(0:Nmax+1): a pair that is outside the
+// cutoff (or is the moved particle itself) is looked up at r_clamp = (Nmax+3.5)*dr, where value and centred
+// difference read only zeros -- its contribution vanishes without a select on every accumulated term.
+constexpr int TAB_PAD = 4;
+__host__ __device__ __forceinline__ int tab_len(int Nmax) { return Nmax + 2 + TAB_PAD; }
 __host__ __device__ __forceinline__ int pidx(int j) { return (j >> 5) * PBLK + (j & 31); }
 __device__ __forceinline__ double* slice(GS* gs, int ib) { return gs->path + (size_t)ib * 3 * cP.NpS; }
 __device__ __forceinline__ double& pth(GS* gs, int k, int ip0, int ib) { return gs->path[(size_t)ib * 3 * cP.NpS + pidx(ip0) + 32 * k]; }
@@ -190,7 +196,7 @@ template <bool SM, int WHICH, bool VSM_FIRST>
 __device__ __forceinline__ double tab(int i) {
     if (SM) {
         extern __shared__ __align__(16) double pigs_smem_base[];
-        const int off = (WHICH == 1 && VSM_FIRST) ? cP.Nmax + 2 : 0;
+        const int off = (WHICH == 1 && VSM_FIRST) ? tab_len(cP.Nmax) : 0;
         return pigs_smem_base[off + i];
     }
     return __ldg((WHICH == 0 ? cP.vtab : cP.logwf) + i);
@@ -499,7 +505,7 @@ __device__ __forceinline__ PairGeom pair_geom(bool valid, double x0, double x1, 
     g.in_pot = valid && (TRAP ? (IS_NEW || r2 <= cP.rcut2) : (r2 <= cP.rcut2));
     g.in_wf = TRAP ? valid : g.in_pot;
     const bool any = (KIND == 2) ? g.in_wf : g.in_pot;
-    double r2c = any ? r2 : cP.rcut2;
+    double r2c = any ? r2 : (TRAP ? cP.rcut2 : cP.rclamp2);
     g.ir = rsqrt_pos(r2c);
     g.k = lk_prep(r2c * g.ir);
     if (TRAP) g.k.i0 = min(g.k.i0, cP.Nmax - 1);
@@ -540,21 +546,22 @@ __device__ __forceinline__ Partner load_partner(const double* Rx, int j) {
 template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
 __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& cur, const double (&xo)[3],
                                           const double (&xn)[3], double& pot, double& psi, double (&fn)[3], double (&fo)[3]) {
+    constexpr bool MASK = TRAP || VPAIR;        // else: masked pairs read the zero tail of the tables
     if (kind == 1) {
         {
             PairGeom g = pair_geom<1, TRAP, true>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z);
             double v, dv;
             if (VPAIR) lk_val_d1_pair(g.k, v, dv); else lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
-            pot += g.in_pot ? v : 0.0;
-            double s = g.in_pot ? dv * g.ir : 0.0;
+            pot += (!MASK || g.in_pot) ? v : 0.0;
+            double s = (!MASK || g.in_pot) ? dv * g.ir : 0.0;
             fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
         }
         {
             PairGeom g = pair_geom<1, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z);
             double v, dv;
             if (VPAIR) lk_val_d1_pair(g.k, v, dv); else lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
-            pot -= g.in_pot ? v : 0.0;
-            double s = g.in_pot ? dv * g.ir : 0.0;
+            pot -= (!MASK || g.in_pot) ? v : 0.0;
+            double s = (!MASK || g.in_pot) ? dv * g.ir : 0.0;
             fo[0] += s * g.d0; fo[1] += s * g.d1; fo[2] += s * g.d2;
         }
     } else {
@@ -565,10 +572,10 @@ __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& c
                                           : pair_geom<0, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z);
         double vn = VPAIR ? lk_val_pair(gn.k) : lk_val<VSM, 0, VSM>(gn.k);
         double vo = VPAIR ? lk_val_pair(go.k) : lk_val<VSM, 0, VSM>(go.k);
-        pot += (gn.in_pot ? vn : 0.0) - (go.in_pot ? vo : 0.0);
+        pot += ((!MASK || gn.in_pot) ? vn : 0.0) - ((!MASK || go.in_pot) ? vo : 0.0);
         if (kind == 2) {
             double wn = lk_val<WSM, 1, VSM && !VPAIR>(gn.k), wo = lk_val<WSM, 1, VSM && !VPAIR>(go.k);
-            psi += (gn.in_wf ? wn : 0.0) - (go.in_wf ? wo : 0.0);
+            psi += ((!MASK || gn.in_wf) ? wn : 0.0) - ((!MASK || go.in_wf) ? wo : 0.0);
         }
     }
 }

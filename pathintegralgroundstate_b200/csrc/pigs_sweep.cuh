@@ -1032,7 +1032,7 @@ PIGS_T __device__ __forceinline__ void sweep_body() {
     extern __shared__ __align__(16) double smem[];
     using VT = VarTraits<VAR>;
     const int T = cA.threads_per_chain, Gn = cA.groups_per_cta;
-    const int ntab = cP.Nmax + 2;
+    const int ntab = tab_len(cP.Nmax);
     double* sp = smem;
     const double* tV = cP.vtab;
     const double* tW = cP.logwf;

@@ -10,7 +10,7 @@ using namespace pigs;
 template <int KINDSEL>
 __global__ void __launch_bounds__(512, 1) k_loop(const double* slices, int nslices, int iters, double* out) {
     extern __shared__ __align__(16) double pigs_smem_base[];
-    const int ntab = cP.Nmax + 2;
+    const int ntab = tab_len(cP.Nmax);
     for (int i = threadIdx.x; i < ntab; i += blockDim.x) { pigs_smem_base[i] = cP.vtab[i]; pigs_smem_base[ntab + i] = cP.logwf[i]; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -52,8 +52,8 @@ int main(int argc, char** argv) {
     P.dim = 3; P.Np = Np; P.Nb = 15; P.S = 31; P.NpS = (Np + 31) & ~31; P.Nmax = 10000;
     double L = cbrt(Np / 0.365);
     for (int k = 0; k < 3; ++k) { P.L[k] = L; P.Lh[k] = L / 2; P.invL[k] = 1 / L; }
-    double rcut = L / 2; P.rcut2 = rcut * rcut; P.dr = rcut / 9999.0; P.inv_dr = 1 / P.dr; P.half_inv_dr2 = 0.5 * P.inv_dr * P.inv_dr; P.dt = 5e-3;
-    std::vector<double> tab(10002), slices((size_t)nslices * 3 * P.NpS);
+    double rcut = L / 2; P.rcut2 = rcut * rcut; P.dr = rcut / 9999.0; P.inv_dr = 1 / P.dr; P.half_inv_dr2 = 0.5 * P.inv_dr * P.inv_dr; P.rclamp2 = (P.Nmax + 3.5) * P.dr * (P.Nmax + 3.5) * P.dr; P.dt = 5e-3;
+    std::vector<double> tab(10006, 0.0), slices((size_t)nslices * 3 * P.NpS);
     for (int i = 0; i < 10002; ++i) { double r = (i + 1) * P.dr; tab[i] = 1.0 / (r * r * r + 0.1); }
     for (auto& v : slices) v = (rand() / (double)RAND_MAX - 0.5) * L;
     double *d_tab, *d_sl, *d_out;
@@ -62,7 +62,7 @@ int main(int argc, char** argv) {
     cudaMemcpy(d_sl, slices.data(), slices.size() * 8, cudaMemcpyHostToDevice);
     P.vtab = d_tab; P.logwf = d_tab;
     cudaMemcpyToSymbol(cP, &P, sizeof P);
-    size_t smem = 2 * 10002 * 8;
+    size_t smem = 2 * 10006 * 8;
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     auto run = [&](auto kern, const char* name) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
