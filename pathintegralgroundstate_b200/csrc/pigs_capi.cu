@@ -81,8 +81,12 @@ static int plan(pigs_ctx* h) {
         int maxt0 = 1024;
         CK(sweep_max_threads(h->mt, p.trap ? 3 : 0, &maxt0));
         long long want = (long long)nsm * maxt0 / (p.n_chains > 0 ? p.n_chains : 1);
+        // ... but a group only has nb x Np/32 independent warp-tasks per evaluation: wider than Np/64 warps
+        // never paid (measured, 512 chains: N=64 T=32/64/128 -> 269/256/226 M bead-updates/s, N=256 -> 138/175/182)
+        int tcap = 32;
+        while (tcap * 2 <= 32 * (p.Np / 64) && tcap < 256) tcap *= 2;
         T = 32;
-        while (T * 2 <= want && T < 256) T *= 2;
+        while (T * 2 <= want && T < tcap) T *= 2;
     }
     if (T != 32 && T != 64 && T != 128 && T != 256 && T != 512) return fail(PIGS_E_ARG, "threads_per_chain must be 0,32,64,128,256,512");
     const size_t gbytes = (grp_smem_bytes(h->P.S, h->P.Np, T / 32) + 15) & ~(size_t)15;
