@@ -740,7 +740,7 @@ static __device__ __noinline__ void LocalEnergy(GS* gs, const double* Rx, double
 // GreenFunction(opt=1) is linear in (Pot, F2), so every (slice, particle) item adds its
 // weighted share directly; no per-slice reduction is needed.  out = E, Ec, Ep.
 template <int VAR>
-static __device__ __noinline__ void ThermEnergy(GS* gs, double* out) {
+static __device__ __forceinline__ void ThermEnergy(GS* gs, double* out) {      // one call site per kernel: inlined (see run_move_body)
     const Grp G = grp();
     const int nitem = 2 * cP.Nb * cP.Np;
     const double dt = cP.dt;
