@@ -29,7 +29,7 @@ GROUPS = dict(
     wavefun=("Nmax", "wf_table", "v_table"),
     jastrow=("Rm",),
     extpot=("a_ho",),
-    cuda=("n_chains", "rng", "threads_per_chain", "table_mode", "gpus", "philox_seed"),
+    cuda=("n_chains", "rng", "threads_per_chain", "table_mode", "gpus", "philox_seed", "action"),
 )
 REQUIRED = ("dim", "Np", "density", "dt", "Nb", "delta_cm", "CMFreq", "sampling", "Nstag", "Nblock", "Nstep", "Nbin",
             "Nk", "Rm")
@@ -107,6 +107,8 @@ def read_vpi_in(text: str) -> dict:
     if isinstance(cfg["sampling"], str):
         cfg["sampling"] = cfg["sampling"].strip()[:3]
     cfg["cuda"] = dict(nl.get("cuda", {}))
+    if "action" in cfg["cuda"]:                    # 'chin' (the reference's live code) | 'primitive' (global_mod.f90:48,67)
+        cfg["action"] = str(cfg["cuda"]["action"])
     return cfg
 
 
