@@ -192,3 +192,31 @@ def test_vpi_cuda_many_chains_philox(tmp_path):
     assert "Markov chains (GPU) :    64" in out and "FINAL RESULTS" in out
     e = np.loadtxt(tmp_path / "e_vpi.out")
     assert e.shape == (2, 4) and np.all(np.isfinite(e))
+
+
+@pytest.mark.gpu
+def test_vpi_cuda_crystal_reads_config_ini(tmp_path):
+    """crystal=T: Np, Lbox and density come from config_ini.in (vpi.f90:101-107), the sites from its tail (vpi_mod.f90:220-228)"""
+    from pathintegralgroundstate_b200 import PigsCuda
+    from pathintegralgroundstate_b200.host import write_config_ini
+    from pathintegralgroundstate_b200.workloads import hcp_lattice
+    R, L = hcp_lattice(2, 2, 2, density=0.48426)          # 32 hcp sites
+    cfg = dict(CWX, Np=32, density=0.48426, crystal=True, Lbox=list(L), Nblock=2, Nstep=6)
+    a, b = tmp_path / "cxx", tmp_path / "py"
+    for d in (a, b):
+        os.makedirs(d)
+        write_config_ini(str(d / "config_ini.in"), R, L, 0.48426)
+    vin = format_vpi_in(dict(cfg, Np=1, density=9.9), cuda=dict(n_chains=1, rng="mt"))     # Np/density in vpi.in are overridden
+    out = _vpi(["--workdir", str(a)], vin)
+    assert "Number of particles :    32" in out
+    VpiDriver(cfg, PigsCuda(cfg, n_chains=1, rng="mt", seed=cfg["seed"]), workdir=str(b), quiet=True).run()
+    _compare_run_dirs(a, b, ["e_vpi.out", "et_vpi.out", "gr_vpi.out", "sk_vpi.out", "fort.99", "checkpoint.dat", "rand_state"])
+    # the Python command line reads config_ini.in the same way
+    import subprocess, sys
+    c = tmp_path / "pycli"
+    os.makedirs(c)
+    write_config_ini(str(c / "config_ini.in"), R, L, 0.48426)
+    r = subprocess.run([sys.executable, "-m", "pathintegralgroundstate_b200.driver", "--workdir", str(c)], input=vin, capture_output=True,
+                       text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    _compare_run_dirs(a, c, ["e_vpi.out", "et_vpi.out", "checkpoint.dat"])
