@@ -197,7 +197,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
         P.a_ho[k] = k < p->dim ? p->a_ho[k] : 1.0;
     }
     P.rcut2 = p->rcut * p->rcut;              // vpi.f90:127
-    P.dr = p->dr; P.inv_dr = 1.0 / p->dr; P.half_inv_dr2 = 0.5 * P.inv_dr * P.inv_dr;
+    P.dr = p->dr; P.inv_dr = 1.0 / p->dr; P.half_inv_dr = 0.5 * P.inv_dr;
     P.rclamp2 = ((double)p->Nmax + 3.5) * p->dr * ((double)p->Nmax + 3.5) * p->dr;
     P.rbin = p->rcut / (double)(float)p->Nbin;   // vpi.f90:128
     P.dt = p->dt; P.delta_cm = p->delta_cm; P.CWorm = p->CWorm; P.density = p->density;

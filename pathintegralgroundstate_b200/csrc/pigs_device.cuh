@@ -65,7 +65,7 @@ struct DevParams {
     //   sig_bis[l]   = sqrt(0.5*(0.5*real(2**l)*dt))           bisection, delta_ib = 2**l     (vpi_mod.f90:906-907)
     double sig_free[MAXS], sig_stage[MAXS], sig_bis[16];
     double half_inv_dt2;
-    double half_inv_dr2;      // 0.5/dr^2 (centred difference of the table)
+    double half_inv_dr;       // 0.5/dr (centred difference of the table, cell coordinates)
     double rclamp2;           // ((Nmax+3.5)*dr)^2: where masked pairs are looked up (zero tail of the tables)
     unsigned long long seed;
     const double* logwf;      // (0:Nmax+1) in global memory
@@ -216,6 +216,15 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
     double p = fma(0.375, e, 0.5);
     return fma(y * e, p, y);                        // y (1 + e/2 + 3e^2/8)
 }
+// sqrt(x) by the same step applied to x*y: one slot and one dependent level less than x * rsqrt_pos(x)
+__device__ __forceinline__ double sqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double r0 = x * y;
+    double e = fma(-r0, y, 1.0);
+    double p = fma(0.375, e, 0.5);
+    return fma(r0 * e, p, r0);
+}
 
 // Interpolate(opt,...) of interpolate.f90:1-45, fast form for the hot loop:
 // x/dx -> x*inv_dx and floor() by the 2^52 trick (no F2I/I2F conversions).
@@ -223,18 +232,18 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
 // harmless.
 struct Lk {
     int i0;          // = ix-1
-    double a1, a2;   // aux1, aux2 of interpolate.f90:14-15
+    double t;        // aux1/dx of interpolate.f90:14: position inside the cell, [0,1)
 };
 __device__ __forceinline__ Lk lk_prep(double r) {
     const double MAGIC = 6755399441055744.0;                 // 2^52 + 2^51
-    double m = fma(r, cP.inv_dr, -0.5) + MAGIC;              // round-to-nearest of (t - 1/2) == floor(t) off grid points
+    double m = fma(r, cP.inv_dr, -0.5) + MAGIC;              // round-to-nearest of (s - 1/2) == floor(s) off grid points
     Lk k;
     k.i0 = max(__double2loint(m), 1);                        // r >= dr always in practice; keeps i0-1 in range
-    double tf = m - MAGIC;
-    k.a1 = fma(-tf, cP.dr, r);
-    k.a2 = cP.dr - k.a1;
+    k.t = fma(r, cP.inv_dr, -(m - MAGIC));                   // s - floor(s), one rounding
     return k;
 }
+// The interpolants in cell coordinates -- (aux1 F(ix) + aux2 F(ix-1))/dx == F(ix-1) + t (F(ix) - F(ix-1)) --
+// two FP64 slots per value instead of four and no aux2; the hot loop is two thirds FP64-pipe bound (ncu).
 // VTable staged as pairs: entry i holds {F(i), F(i+1)} (16-byte aligned), so a linear
 // interpolant is ONE shared-memory request instead of two (ncu: 2 bank-conflict
 // cycles per LDS.64 on the random table indices of a warp).
@@ -244,28 +253,28 @@ __device__ __forceinline__ double2 tabpair(int i) {
 }
 __device__ __forceinline__ double lk_val_pair(const Lk& k) {
     double2 t = tabpair(k.i0);
-    return (k.a1 * t.y + k.a2 * t.x) * cP.inv_dr;
+    return fma(k.t, t.y - t.x, t.x);
+}
+// value and centred first difference (opt 0 and 1): d1 = (Fa - Fb)/(2 dx) with Fa, Fb the interpolants one
+// cell up and one cell down
+__device__ __forceinline__ void lk_d1_from(double t, double fm, double f0, double f1, double f2, double& v, double& d1) {
+    v = fma(t, f1 - f0, f0);
+    double b = fma(t, (f2 + fm) - (f1 + f0), f1 - fm);       // Fa - Fb = (f1-fm) + t ((f2-f1) - (f0-fm))
+    d1 = b * cP.half_inv_dr;
 }
 __device__ __forceinline__ void lk_val_d1_pair(const Lk& k, double& v, double& d1) {
     double2 lo = tabpair(k.i0 - 1), hi = tabpair(k.i0 + 1);      // {fm,f0}, {f1,f2}
-    double Fc = k.a1 * hi.x + k.a2 * lo.y;
-    double Fb = k.a1 * lo.y + k.a2 * lo.x;
-    double Fa = k.a1 * hi.y + k.a2 * hi.x;
-    v = Fc * cP.inv_dr;
-    d1 = (Fa - Fb) * cP.half_inv_dr2;
+    lk_d1_from(k.t, lo.x, lo.y, hi.x, hi.y, v, d1);
 }
 template <bool SM, int WHICH, bool VF>
 __device__ __forceinline__ double lk_val(const Lk& k) {   // opt 0
-    return (k.a1 * tab<SM, WHICH, VF>(k.i0 + 1) + k.a2 * tab<SM, WHICH, VF>(k.i0)) * cP.inv_dr;
+    double f0 = tab<SM, WHICH, VF>(k.i0), f1 = tab<SM, WHICH, VF>(k.i0 + 1);
+    return fma(k.t, f1 - f0, f0);
 }
 template <bool SM, int WHICH, bool VF>
 __device__ __forceinline__ void lk_val_d1(const Lk& k, double& v, double& d1) {   // opt 0 and 1
     double fm = tab<SM, WHICH, VF>(k.i0 - 1), f0 = tab<SM, WHICH, VF>(k.i0), f1 = tab<SM, WHICH, VF>(k.i0 + 1), f2 = tab<SM, WHICH, VF>(k.i0 + 2);
-    double Fc = k.a1 * f1 + k.a2 * f0;
-    double Fb = k.a1 * f0 + k.a2 * fm;
-    double Fa = k.a1 * f2 + k.a2 * f1;
-    v = Fc * cP.inv_dr;
-    d1 = (Fa - Fb) * cP.half_inv_dr2;
+    lk_d1_from(k.t, fm, f0, f1, f2, v, d1);
 }
 
 // Interpolate opt 0, 1 and 2 in the reference's exact operation order, true
@@ -506,8 +515,13 @@ __device__ __forceinline__ PairGeom pair_geom(bool valid, double x0, double x1, 
     g.in_wf = TRAP ? valid : g.in_pot;
     const bool any = (KIND == 2) ? g.in_wf : g.in_pot;
     double r2c = any ? r2 : (TRAP ? cP.rcut2 : cP.rclamp2);
-    g.ir = rsqrt_pos(r2c);
-    g.k = lk_prep(r2c * g.ir);
+    if (KIND == 1) {           // the force needs 1/r as well
+        g.ir = rsqrt_pos(r2c);
+        g.k = lk_prep(r2c * g.ir);
+    } else {
+        g.ir = 0.0;
+        g.k = lk_prep(sqrt_pos(r2c));
+    }
     if (TRAP) g.k.i0 = min(g.k.i0, cP.Nmax - 1);
     return g;
 }

@@ -797,8 +797,7 @@ static __device__ __forceinline__ void ThermEnergy(GS* gs, double* out) {      /
                 }
                 double r2 = d0 * d0 + d1 * d1 + d2 * d2;
                 if (PIGS_TRAP || r2 <= cP.rcut2) {
-                    double ir = rsqrt_pos(r2);
-                    Lk k = lk_prep(r2 * ir);
+                    Lk k = lk_prep(sqrt_pos(r2));
                     if (PIGS_TRAP) k.i0 = min(k.i0, cP.Nmax - 1);
                     pot += 2.0 * (PIGS_VPAIR ? lk_val_pair(k) : lk_val<PIGS_VSM, 0, PIGS_VSM>(k));
                 }

@@ -52,7 +52,7 @@ int main(int argc, char** argv) {
     P.dim = 3; P.Np = Np; P.Nb = 15; P.S = 31; P.NpS = (Np + 31) & ~31; P.Nmax = 10000;
     double L = cbrt(Np / 0.365);
     for (int k = 0; k < 3; ++k) { P.L[k] = L; P.Lh[k] = L / 2; P.invL[k] = 1 / L; }
-    double rcut = L / 2; P.rcut2 = rcut * rcut; P.dr = rcut / 9999.0; P.inv_dr = 1 / P.dr; P.half_inv_dr2 = 0.5 * P.inv_dr * P.inv_dr; P.rclamp2 = (P.Nmax + 3.5) * P.dr * (P.Nmax + 3.5) * P.dr; P.dt = 5e-3;
+    double rcut = L / 2; P.rcut2 = rcut * rcut; P.dr = rcut / 9999.0; P.inv_dr = 1 / P.dr; P.half_inv_dr = 0.5 * P.inv_dr; P.rclamp2 = (P.Nmax + 3.5) * P.dr * (P.Nmax + 3.5) * P.dr; P.dt = 5e-3;
     std::vector<double> tab(10006, 0.0), slices((size_t)nslices * 3 * P.NpS);
     for (int i = 0; i < 10002; ++i) { double r = (i + 1) * P.dr; tab[i] = 1.0 / (r * r * r + 0.1); }
     for (auto& v : slices) v = (rand() / (double)RAND_MAX - 0.5) * L;
