@@ -236,7 +236,7 @@ struct Lk {
 };
 __device__ __forceinline__ Lk lk_prep(double r) {
     const double MAGIC = 6755399441055744.0;                 // 2^52 + 2^51
-    double m = fma(r, cP.inv_dr, -0.5) + MAGIC;              // round-to-nearest of (s - 1/2) == floor(s) off grid points
+    double m = __fma_rd(r, cP.inv_dr, MAGIC);                // MAGIC + floor(s): the round-down FMA floors in one slot
     Lk k;
     k.i0 = max(__double2loint(m), 1);                        // r >= dr always in practice; keeps i0-1 in range
     k.t = fma(r, cP.inv_dr, -(m - MAGIC));                   // s - floor(s), one rounding
