@@ -297,15 +297,6 @@ __device__ __forceinline__ void lk_exact_d1_d2(const double* F, double x, double
     d1 = 0.5 * (Fa - Fb) * cP.inv_dr;
     d2 = __ddiv_rn(__dadd_rn(__dadd_rn(Fa, -__dmul_rn(2.0, Fc)), Fb), __dmul_rn(dx, dx));
 }
-template <bool SM>
-__device__ __forceinline__ double lk_exact_val(const double* F, double x) {
-    const double dx = cP.dr;
-    int ix = (int)__ddiv_rn(x, dx) + 1;
-    ix = max(2, min(ix, cP.Nmax));
-    double aux1 = __dadd_rn(x, -__dmul_rn((double)(ix - 1), dx));
-    double aux2 = __dadd_rn(dx, -aux1);
-    return __ddiv_rn(__dadd_rn(__dmul_rn(aux1, tld<SM>(F, ix)), __dmul_rn(aux2, tld<SM>(F, ix - 1))), dx);
-}
 
 // ------------------------------------------------------------------ geometry
 // MinimumImage / BoundaryConditions (pbc_mod.f90:11-52): one shift, '>' first
@@ -528,8 +519,6 @@ __device__ __forceinline__ PairGeom pair_geom(bool valid, double x0, double x1, 
 
 // 0 interior slice without force term, 1 odd slice (Chin force term), 2 end slice (Jastrow)
 __device__ __forceinline__ int bead_kind(int ib) { return (ib == 0 || ib == 2 * cP.Nb) ? 2 : (cP.primitive ? 0 : (ib & 1)); }
-// counting class of a bead-update (even / odd / end), independent of the propagator
-__device__ __forceinline__ int bead_class(int ib) { return (ib == 0 || ib == 2 * cP.Nb) ? 2 : (ib & 1); }
 
 // coherent global load of a path coordinate (the path is written by this group
 // during the kernel, so no .nc; an explicit ld.global avoids the generic-address
