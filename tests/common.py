@@ -14,6 +14,8 @@ C1 = dict(dim=3, Np=8, density=1.0, trap=True, a_ho=[1.0, 1.0, 1.0], dt=0.05, Nb
 C2 = dict(dim=3, Np=64, density=0.365, trap=False, dt=5e-3, Nb=15, seed=1982, delta_cm=0.12, CMFreq=1,
           sampling="bis", Lstag=14, Nlev=3, Nstag=5, Nbin=100, Nk=50, swapping=True, CWorm=0.0, Nobdm=1, Npw=0,
           Nmax=10000, wf_table=True, v_table=True, Rm=1.2)
+# the input file the reference ships (vpi.in): N=64, 2M=64 beads, 16-link bisection, 32-link worm moves, worm on
+CREF = dict(C2, Nb=32, Lstag=32, Nlev=4, CWorm=0.5, Nobdm=10)
 # C3: liquid He-4 N=256, worm on                                   -- configs[2]
 C3 = dict(C2, Np=256, CWorm=0.5, Nobdm=10)
 # small worm configuration for fast replay tests

@@ -312,6 +312,13 @@ def test_run_block_replay_worm_staging():
     assert tot["acc_head"] > 0 and tot["acc_tail"] > 0 and tot["acc_bd"] > 0
 
 
+def test_run_block_replay_reference_default_input():
+    """the parameters of the vpi.in the reference ships: Nb = Lstag = 32, Nlev = 4, CWorm = 0.5, Nobdm = 10"""
+    from tests.common import CREF
+    _, _, tot = _replay_block(CREF, nchain=2, nstep=4, nblock=2)
+    assert tot["try_stag"] > 0 and tot["acc_bd"] > 0 and tot["acc_head"] > 0
+
+
 def test_run_block_replay_c2():
     _replay_block(C2, nchain=2, nstep=2, nblock=1)
 
