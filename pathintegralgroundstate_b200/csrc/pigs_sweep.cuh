@@ -78,6 +78,32 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         gs->cnt[C_UPD_EVEN] += nb - nodd - nend;
     }
     const int nw = G.nwarps;
+#ifndef PIGS_NO_WARP_FASTPATH
+    if (nw == 1) {
+        // one warp per chain (the production shape): beads in order, the whole partner range per bead; no task
+        // decomposition, no partial-sum exchange
+        const int lane = G.lane;
+        const bool have = lane < cP.Np;
+        Partner first;
+        first.x = first.y = first.z = 0.0;
+        if (have) first = load_partner(slice(gs, b0), lane);
+        double Sw = 0.0;
+        for (int m = 0; m < nb; ++m) {
+            const int ib = b0 + m * bstride;
+            double xo[3], xn[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { xo[k] = so(gs, k, ib); xn[k] = sn(gs, k, ib); }
+            const Partner cur = first;
+            if (m + 1 < nb && have) first = load_partner(slice(gs, ib + bstride), lane);
+            if (roll && lane == 0 && m + cA.pfdist < nb) prefetch_slice_L2(slice(gs, ib + cA.pfdist * bstride));
+            const double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM, PIGS_VPAIR>(slice(gs, ib), ip0, ib, lane, 32, lane == 0, xo, xn,
+                                                                                 lane, nullptr, cur);
+            const double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
+            Sw += w * t;
+        }
+        return Sw;
+    }
+#endif
     int split = 1;
     if (nb < nw) {
         const int nch = (cP.Np + 31) >> 5;
