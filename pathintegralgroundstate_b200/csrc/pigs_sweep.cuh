@@ -86,17 +86,19 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         const bool have = lane < cP.Np;
         Partner first;
         first.x = first.y = first.z = 0.0;
-        if (have) first = load_partner(slice(gs, b0), lane);
+        const double* Rx = slice(gs, b0);                                  // walks the evaluated slices
+        const long long sstride = (long long)bstride * 3 * cP.NpS, pfoff = (long long)cA.pfdist * sstride;
+        if (have) first = load_partner(Rx, lane);
         double Sw = 0.0;
-        for (int m = 0; m < nb; ++m) {
+        for (int m = 0; m < nb; ++m, Rx += sstride) {
             const int ib = b0 + m * bstride;
             double xo[3], xn[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) { xo[k] = so(gs, k, ib); xn[k] = sn(gs, k, ib); }
             const Partner cur = first;
-            if (m + 1 < nb && have) first = load_partner(slice(gs, ib + bstride), lane);
-            if (roll && lane == 0 && m + cA.pfdist < nb) prefetch_slice_L2(slice(gs, ib + cA.pfdist * bstride));
-            const double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM, PIGS_VPAIR>(slice(gs, ib), ip0, ib, lane, 32, lane == 0, xo, xn,
+            if (m + 1 < nb && have) first = load_partner(Rx + sstride, lane);
+            if (roll && lane == 0 && m + cA.pfdist < nb) prefetch_slice_L2(Rx + pfoff);
+            const double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM, PIGS_VPAIR>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn,
                                                                                  lane, nullptr, cur);
             const double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
             Sw += w * t;
