@@ -512,6 +512,13 @@ int main(int argc, char** argv) {
         printf("dim %d Np %d Nb %d Nmax %d sampling %s n_chains %d rng %s\n", dim, Np, Nb, Nmax, c.sampling.c_str(), c.n_chains, c.rng.c_str());
         printf("Lbox %.17g %.17g %.17g\nrcut %.17g\ndr %.17g\nrbin %.17g\ndensity %.17g\ndelta_cm %.17g\n", g.Lbox[0], g.Lbox[1], g.Lbox[2],
                g.rcut, g.dr, g.rbin, g.density, g.delta_cm);
+        printf("config resume %d seed %d CMFreq %d Lstag %d Nlev %d Nstag %d Nblock %d Nstep %d Nbin %d Nk %d swapping %d Nobdm %d Npw %d "
+               "trap %d crystal %d wf_table %d v_table %d threads_per_chain %d table_mode %d\n",
+               (int)c.resume, c.seed, c.CMFreq, c.Lstag, c.Nlev, c.Nstag, c.Nblock, c.Nstep, c.Nbin, c.Nk, (int)c.swapping, c.Nobdm, c.Npw,
+               (int)c.trap, (int)c.crystal, (int)c.wf_table, (int)c.v_table, c.threads_per_chain, c.table_mode);
+        printf("reals dt %.17g CWorm %.17g Rm %.17g a_ho", c.dt, c.CWorm, c.Rm);
+        for (double a : c.a_ho) printf(" %.17g", a);
+        printf("\naction %s\n", c.action.empty() ? "chin" : c.action.c_str());
         return 0;
     }
 

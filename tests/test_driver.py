@@ -220,3 +220,43 @@ def test_vpi_cuda_crystal_reads_config_ini(tmp_path):
                        text=True, cwd=ROOT, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     _compare_run_dirs(a, c, ["e_vpi.out", "et_vpi.out", "checkpoint.dat"])
+
+
+NASTY_VPI_IN = """! leading comment with & and / characters
+ &SYSTEM DIM=3, NP = 8 , Density = 1.0D0, TRAP = .TRUE. , crystal=.false. /
+&samp
+  resume = .FALSE. ! comment after value
+  dt = 5.0d-2, Nb=20, seed = 7
+  delta_cm = 0.5 , CMFreq = 1, sampling = "bis"
+  Lstag = 16, Nlev = 3,
+  Nstag = 5, Nblock = 2, Nstep = 3, Nbin = 10, Nk = 4
+&end
+&obdm swapping=T CWorm=0.25 Nobdm=1 Npw=0 /
+&wavefun Nmax=1000, wf_table=T, v_table=T /
+&jastrow
+ Rm = 1.2 /
+&extpot a_ho(1:3) = 1.0, 2.0d0 , 0.5 /
+&cuda n_chains = 5, rng = 'MT', action = 'primitive' /
+"""
+
+
+def test_namelist_parsers_agree_on_free_form_input(tmp_path):
+    """upper case, .TRUE./T, D exponents, '&end', inline comments, missing commas, index ranges, double quotes"""
+    c = read_vpi_in(NASTY_VPI_IN)
+    out = _vpi(["--tables-only", "--workdir", str(tmp_path), "--potential", "zero"], NASTY_VPI_IN).splitlines()
+    head = out[0].split()
+    assert head[1::2] == ["3", "8", "20", "1000", "bis", "5", "mt"]
+    assert (c["dim"], c["Np"], c["Nb"], c["Nmax"], c["sampling"], c["cuda"]["n_chains"], c["cuda"]["rng"].lower()) == (3, 8, 20, 1000, "bis", 5, "mt")
+    cfgline = [ln for ln in out if ln.startswith("config ")][0].split()[1:]
+    got = dict(zip(cfgline[0::2], (int(v) for v in cfgline[1::2])))
+    for k in ("resume", "seed", "CMFreq", "Lstag", "Nlev", "Nstag", "Nblock", "Nstep", "Nbin", "Nk", "swapping", "Nobdm", "Npw", "trap",
+              "crystal", "wf_table", "v_table"):
+        assert got[k] == int(c[k]), k
+    reals = [ln for ln in out if ln.startswith("reals ")][0].split()
+    assert float(reals[2]) == c["dt"] == 0.05 and float(reals[4]) == c["CWorm"] == 0.25 and float(reals[6]) == c["Rm"]
+    assert [float(t) for t in reals[8:]] == c["a_ho"] == [1.0, 2.0, 0.5]
+    assert out[-1] == "action primitive" and c["action"] == "primitive"
+    g = derive_geometry(c)
+    kv = {ln.split()[0]: ln.split()[1:] for ln in out[1:]}
+    for k in ("rcut", "dr", "rbin", "density", "delta_cm"):
+        assert float(kv[k][0]) == g[k], k
