@@ -98,7 +98,10 @@ double Interpolate(int opt, int N, double dx, const double* F, double x) {
 
 /* ---------------------------------------------------------------- system_mod.f90 */
 double LogPsi(int opt, double Rm, double rij) {           /* system_mod.f90:38-66 */
-    double q5 = ipow(Rm / rij, 5);
+    /* (Rm/rij)**5 as gfortran/GCC expand a constant integer power (the powi table): x^5 = (x * x^2) * x^2 --
+     * pinned by the machine translation of system_mod.f90 (oracle/_ref, tests/test_ref_pin.py) */
+    const double q = Rm / rij, q2 = q * q, q3 = q * q2;
+    double q5 = q3 * q2;
     if (opt == 0) return -0.5 * q5;
     if (opt == 1) return 2.5 * q5 / rij;
     return -15.0 * q5 / (rij * rij);

@@ -8,13 +8,19 @@
  * import, link or call it: only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs do.
  *
- * PARITY PINNING: the reference ships no tests, golden vectors or fixtures
- * and no Fortran compiler exists in this image, so the oracle cannot be run
- * against the reference binary.  It is pinned by (i) published MT19937 (1998)
- * outputs, (ii) analytic values of the Aziz HFD-B(HE) potential and McMillan
- * factor, (iii) the analytic zero-variance local energy of the harmonic trap,
- * (iv) self-consistency: Delta S from UpdateAction == difference of full
- * actions.  Parity against the reference itself is therefore "unpinned".
+ * PARITY PINNING: the reference ships no tests, golden vectors or fixtures and no Fortran compiler exists in
+ * this image, so the reference BINARY cannot be run.  The oracle is pinned instead by oracle/_ref: the
+ * reference's own Fortran sources, machine-translated statement by statement into C++ by the committed recipe
+ * oracle/f90toc/f90toc.py (read from /root/reference where they lie; the generated file is git-ignored) and
+ * compiled with the oracle's flags.  tests/test_ref_pin.py demands BIT EQUALITY between that translation and this
+ * oracle: leaf functions, tables, the MT19937 stream (the translated generator reproduces the published 1998
+ * head 3510405877, 4290933890), UpdateAction, the estimators, each of the 14 moves from identical state and
+ * stream, and the complete `./vpi < vpi.in` program block by block (worm open/close/swap all accepted);
+ * tests/golden/ref_golden.json holds vectors taken from the translation for boxes without the reference.
+ * (The pin found one discrepancy in round 2 -- (Rm/r)**5 is (x*x^2)*x^2 in gfortran's expansion, not a left-to-right
+ * product: 1 ulp in a third of the Jastrow table entries -- now fixed here and in the product's table generators.)
+ * What the pin cannot see: gfortran's own code generation beyond IEEE semantics and the documented expansion of
+ * integer powers (GCC's powi table), and list-directed output formatting.
  *
  * All indices crossing this interface are Fortran-style: particles ip=1..Np,
  * beads ib=0..2*Nb, arrays column-major Path(dim,Np,0:2*Nb), xend(dim,2),

@@ -195,7 +195,12 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
         P.invL[k] = used ? 1.0 / p->Lbox[k] : 0.0;
         P.qbin[k] = used ? 2.0 * std::acos(-1.0) / p->Lbox[k] : 0.0;   // vpi.f90:119
         P.a_ho[k] = k < p->dim ? p->a_ho[k] : 1.0;
+        unsigned long long bits;
+        std::memcpy(&bits, &P.Lh[k], sizeof bits);
+        const unsigned hi = (unsigned)(bits >> 32);
+        std::memcpy(&P.LhF[k], &hi, sizeof hi);             // high word of L/2 as a float (mimg_hi)
     }
+    P.tabW_off = tab_len(p->Nmax) * (int)sizeof(double);
     P.rcut2 = p->rcut * p->rcut;              // vpi.f90:127
     P.dr = p->dr; P.inv_dr = 1.0 / p->dr; P.half_inv_dr = 0.5 * P.inv_dr;
     P.rclamp2 = ((double)p->Nmax + 3.5) * p->dr * ((double)p->Nmax + 3.5) * p->dr;

@@ -67,6 +67,8 @@ struct DevParams {
     double half_inv_dt2;
     double half_inv_dr;       // 0.5/dr (centred difference of the table, cell coordinates)
     double rclamp2;           // ((Nmax+3.5)*dr)^2: where masked pairs are looked up (zero tail of the tables)
+    float LhF[3];             // high word of L/2 reinterpreted as float (mimg_hi)
+    int tabW_off;             // byte offset of the LogWF copy behind the VTable copy in shared memory
     unsigned long long seed;
     const double* logwf;      // (0:Nmax+1) in global memory
     const double* vtab;
@@ -530,6 +532,11 @@ __device__ __forceinline__ double ldpath(const double* p) {
     asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ double ldpath_ca(const double* p) {
+    double v;
+    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
 struct Partner {
     double x, y, z;
 };
@@ -614,6 +621,173 @@ PIGS_PRAGMA_UNROLL
     }
 }
 
+
+// ------------------------------------------------------------------ partner loop, second generation
+// Compile-time selection of the loop variants (bit mask, measured with scripts/loopbench.cu on B200):
+//   1  partner registers are reloaded in place right after their last use (no cur/nxt copy: -9 MOV, -6 registers)
+//   2  the moved particle excludes itself by a poisoned x coordinate (r^2 = inf -> zero tail) instead of two
+//      selects per position
+//   4  wrap count of the minimum image from a compare on the high word of d (2 FP64 slots per component, not 4)
+//   8  table reads through explicit ld.shared with a 32-bit base (no per-iteration window-base recomputation)
+#ifndef PIGS_LOOPV
+#define PIGS_LOOPV 0
+#endif
+
+// d - L*q with q = -1, 0, +1 decided on the HIGH WORD of d: |d| > L/2 is judged with a resolution of 2^-20
+// relative.  A component inside the band (L/2, L/2 (1 + 2^-20)] keeps the far image; such a pair lies beyond the
+// cutoff unless its transverse distance is below ~1e-3 sigma, and then both images sit at the cutoff radius:
+// probability ~1e-12 per pair evaluation, effect |V(rcut)| dt ~ 1e-5 on DeltaS (documented in DESIGN.md section 5).
+__device__ __forceinline__ int mimg_one_hi() {
+    int v = 0x3ff00000;
+    asm("" : "+r"(v));          // opaque: stays in a register instead of becoming a second immediate
+    return v;
+}
+__device__ __forceinline__ double mimg_hi(double d, double L, float LhF) {
+    const int hi = __double2hiint(d);
+    int one;                                                   // (hi & sign) | 1.0 as ONE LOP3: the second constant in a register
+    asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(one) : "r"(hi), "r"(mimg_one_hi()));
+    const int qhi = (fabsf(__int_as_float(hi)) > LhF) ? one : 0;
+    return fma(-__hiloint2double(qhi, 0), L, d);
+}
+struct Pos2 {          // geometry of one position against one partner
+    double d0, d1, d2, ir;
+    Lk k;
+};
+// One Newton step on the hardware seed (MUFU.RSQ64H, >= 20 bits): relative error <= 1.5 * 2^-40 ~ 1.4e-12 in r and
+// 1/r -- three dependent FP64 latencies instead of four, one slot less.  (The three-term step of rsqrt_pos /
+// sqrt_pos gives 2^-52; 1e-12 in r moves DeltaS by < 1e-13, inside the 1e-10 parity budget.)
+__device__ __forceinline__ double sqrt_q(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double r0 = x * y;
+    const double h = 0.5 * r0;
+    const double e = fma(-r0, y, 1.0);
+    return fma(h, e, r0);
+}
+__device__ __forceinline__ void rsqrt_sqrt_q(double x, double& ir, double& r) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double r0 = x * y;
+    const double e = fma(-r0, y, 1.0);
+    ir = fma(0.5 * y, e, y);
+    r = fma(0.5 * r0, e, r0);
+}
+template <bool NEED_IR>
+__device__ __forceinline__ Pos2 pos_geom(double d0, double d1, double d2) {
+    Pos2 g;
+    if (PIGS_LOOPV & 4) {
+        g.d0 = mimg_hi(d0, cP.L[0], cP.LhF[0]); g.d1 = mimg_hi(d1, cP.L[1], cP.LhF[1]); g.d2 = mimg_hi(d2, cP.L[2], cP.LhF[2]);
+    } else {
+        g.d0 = mimg_fast(d0, cP.L[0], cP.invL[0]); g.d1 = mimg_fast(d1, cP.L[1], cP.invL[1]); g.d2 = mimg_fast(d2, cP.L[2], cP.invL[2]);
+    }
+    const double r2 = g.d0 * g.d0 + g.d1 * g.d1 + g.d2 * g.d2;
+    if (PIGS_LOOPV & 32) {
+        // the cutoff acts on the table INDEX, off the critical path: sqrt of the unclamped r^2 (finite: the self
+        // partner is poisoned with 1e150, not infinity), then i0 = zero tail unless r^2 <= rcut^2 (Q24)
+        const bool in = r2 <= cP.rcut2;
+        double r;
+        if (NEED_IR) { if (PIGS_LOOPV & 16) rsqrt_sqrt_q(r2, g.ir, r); else { g.ir = rsqrt_pos(r2); r = r2 * g.ir; } }
+        else { g.ir = 0.0; r = (PIGS_LOOPV & 16) ? sqrt_q(r2) : sqrt_pos(r2); }
+        const double MAGIC = 6755399441055744.0;
+        const double m = __fma_rd(r, cP.inv_dr, MAGIC);
+        g.k.i0 = in ? __double2loint(m) : cP.Nmax + 3;
+        g.k.t = fma(r, cP.inv_dr, -(m - MAGIC));
+        return g;
+    }
+    const double r2c = (r2 <= cP.rcut2) ? r2 : cP.rclamp2;        // beyond the cutoff, poisoned or NaN: zero tail (Q24)
+    if (NEED_IR) {
+        if (PIGS_LOOPV & 16) { double r; rsqrt_sqrt_q(r2c, g.ir, r); g.k = lk_prep(r); }
+        else { g.ir = rsqrt_pos(r2c); g.k = lk_prep(r2c * g.ir); }
+    } else {
+        g.ir = 0.0;
+        g.k = lk_prep((PIGS_LOOPV & 16) ? sqrt_q(r2c) : sqrt_pos(r2c));
+    }
+    return g;
+}
+template <bool SM, int WHICH, bool VF>
+__device__ __forceinline__ double lk2_val(const Lk& k, unsigned sb) {
+    if (SM && (PIGS_LOOPV & 8)) {
+        const unsigned a = sb + ((unsigned)k.i0 << 3);
+        double f0, f1;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(f0) : "r"(a));
+        asm("ld.shared.f64 %0, [%1+8];" : "=d"(f1) : "r"(a));
+        return fma(k.t, f1 - f0, f0);
+    }
+    return lk_val<SM, WHICH, VF>(k);
+}
+template <bool SM, int WHICH, bool VF>
+__device__ __forceinline__ void lk2_val_d1(const Lk& k, unsigned sb, double& v, double& d1) {
+    if (SM && (PIGS_LOOPV & 8)) {
+        const unsigned a = sb + ((unsigned)k.i0 << 3);
+        double fm, f0, f1, f2;
+        asm("ld.shared.f64 %0, [%1+-8];" : "=d"(fm) : "r"(a));
+        asm("ld.shared.f64 %0, [%1];" : "=d"(f0) : "r"(a));
+        asm("ld.shared.f64 %0, [%1+8];" : "=d"(f1) : "r"(a));
+        asm("ld.shared.f64 %0, [%1+16];" : "=d"(f2) : "r"(a));
+        lk_d1_from(k.t, fm, f0, f1, f2, v, d1);
+        return;
+    }
+    lk_val_d1<SM, WHICH, VF>(k, v, d1);
+}
+// both positions of the displaced bead against ONE partner; dn/dq = x_new - r_j, x_old - r_j before the minimum image
+template <bool VSM, bool WSM>
+__device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW, double dn0, double dn1, double dn2, double dq0,
+                                           double dq1, double dq2, double& pot, double& psi, double (&fn)[3], double (&fo)[3]) {
+    if (kind == 1) {
+        {
+            const Pos2 g = pos_geom<true>(dn0, dn1, dn2);
+            double v, dv;
+            lk2_val_d1<VSM, 0, VSM>(g.k, sbV, v, dv);
+            pot += v;
+            const double s = dv * g.ir;
+            fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
+        }
+        {
+            const Pos2 g = pos_geom<true>(dq0, dq1, dq2);
+            double v, dv;
+            lk2_val_d1<VSM, 0, VSM>(g.k, sbV, v, dv);
+            pot -= v;
+            const double s = dv * g.ir;
+            fo[0] += s * g.d0; fo[1] += s * g.d1; fo[2] += s * g.d2;
+        }
+    } else {
+        const Pos2 gn = pos_geom<false>(dn0, dn1, dn2);
+        const Pos2 go = pos_geom<false>(dq0, dq1, dq2);
+        pot += lk2_val<VSM, 0, VSM>(gn.k, sbV) - lk2_val<VSM, 0, VSM>(go.k, sbV);
+        if (kind == 2) psi += lk2_val<WSM, 1, VSM>(gn.k, sbW) - lk2_val<WSM, 1, VSM>(go.k, sbW);
+    }
+}
+template <bool VSM, bool WSM>
+__device__ __forceinline__ void pair_loop2(int kind, const double* Rx, int ip0, int j0, int jstride, const double (&xo)[3],
+                                           const double (&xn)[3], Partner cur, double& pot, double& psi, double (&fn)[3],
+                                           double (&fo)[3]) {
+    const double* p = Rx + pidx(j0);
+    const int pstep = 3 * jstride;
+    const int self_left = cP.Np - ip0;
+    unsigned sbV = 0, sbW = 0;
+    if (PIGS_LOOPV & 8) {
+        extern __shared__ __align__(16) double pigs_smem_base[];
+        sbV = (unsigned)__cvta_generic_to_shared(pigs_smem_base);
+        sbW = sbV + (unsigned)cP.tabW_off;
+    }
+PIGS_PRAGMA_UNROLL
+    for (int left = cP.Np - j0; left > 0; left -= jstride) {
+        if (left == self_left) cur.x = 1e150;                   // the moved particle itself: r^2 ~ 1e268+ -> zero tail
+        const double dn0 = xn[0] - cur.x, dn1 = xn[1] - cur.y, dn2 = xn[2] - cur.z;
+        const double dq0 = xo[0] - cur.x, dq1 = xo[1] - cur.y, dq2 = xo[2] - cur.z;
+        p += pstep;
+        if (PIGS_LOOPV & 64) {       // L1 prefetch two blocks ahead (6 lines of 128 B per [3][32] block), L1-allocating loads
+            if (left > 2 * jstride && (threadIdx.x & 31) < 6)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(p + pstep - ((threadIdx.x & 31) )) + ((threadIdx.x & 31) << 7)));
+        }
+        if (left > jstride) {
+            if (PIGS_LOOPV & (64 | 128)) { cur.x = ldpath_ca(p); cur.y = ldpath_ca(p + PY); cur.z = ldpath_ca(p + PZ); }
+            else { cur.x = ldpath(p); cur.y = ldpath(p + PY); cur.z = ldpath(p + PZ); }      // in place, one iteration ahead
+        }
+        pair_body2<VSM, WSM>(kind, sbV, sbW, dn0, dn1, dn2, dq0, dq1, dq2, pot, psi, fn, fo);
+    }
+}
+
 // DeltaS of UpdateAction from the eight reduced values [pot, psi, Fnew(3), Fold(3)]
 // (GreenFunction opt 0, global_mod.f90:29-46).
 __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
@@ -650,7 +824,8 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
             }
         }
     }
-    pair_loop<TRAP, VSM, WSM, VPAIR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
+    if (PIGS_LOOPV != 0 && !TRAP && !VPAIR) pair_loop2<VSM, WSM>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
+    else pair_loop<TRAP, VSM, WSM, VPAIR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
     if (kind == 0) {
         double v = warp_sum(pot);
         if (!part) return cP.wS[ib & 1] * v;

@@ -352,8 +352,8 @@ double aziz_hfdhe2(double r) {      // Aziz I HFDHE2 (the commented-out alternat
     return V0 * (A * std::exp(-alpha * d) - (C6 + C8 / d2 + C10 / d4) * Hx / d6);
 }
 double mcmillan_logpsi(double r, double Rm) {      // LogPsi(0,Rm,r) (system_mod.f90:38-66)
-    const double q = Rm / r;
-    return -0.5 * (q * q * q * q * q);
+    const double q = Rm / r, q2 = q * q;
+    return -0.5 * ((q * q2) * q2);        // x**5 as gfortran expands it: (x * x^2) * x^2
 }
 // JastrowTable / PotentialTable (vpi_mod.f90:84-145): entry i holds f((i-1)*dr), pads F(0)=F(2), F(Nmax+1)=F(Nmax)
 template <class F>

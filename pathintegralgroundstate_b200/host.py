@@ -206,7 +206,8 @@ def mcmillan_logpsi(r, Rm):
     r = np.asarray(r, dtype=np.float64)
     with np.errstate(all="ignore"):
         q = Rm / r
-        return -0.5 * (q * q * q * q * q)
+        q2 = q * q
+        return -0.5 * ((q * q2) * q2)        # x**5 as gfortran expands it: (x * x^2) * x^2
 
 
 def make_table(f, rmax: float, Nmax: int, shift_free: bool = False) -> np.ndarray:

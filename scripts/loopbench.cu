@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
+#include <cstring>
 using namespace pigs;
 
 template <int KINDSEL>
@@ -51,8 +52,9 @@ int main(int argc, char** argv) {
     DevParams P; memset(&P, 0, sizeof P);
     P.dim = 3; P.Np = Np; P.Nb = 15; P.S = 31; P.NpS = (Np + 31) & ~31; P.Nmax = 10000;
     double L = cbrt(Np / 0.365);
-    for (int k = 0; k < 3; ++k) { P.L[k] = L; P.Lh[k] = L / 2; P.invL[k] = 1 / L; }
-    double rcut = L / 2; P.rcut2 = rcut * rcut; P.dr = rcut / 9999.0; P.inv_dr = 1 / P.dr; P.half_inv_dr = 0.5 * P.inv_dr; P.rclamp2 = (P.Nmax + 3.5) * P.dr * (P.Nmax + 3.5) * P.dr; P.dt = 5e-3;
+    for (int k = 0; k < 3; ++k) { P.L[k] = L; P.Lh[k] = L / 2; P.invL[k] = 1 / L; unsigned long long b; memcpy(&b, &P.Lh[k], 8); unsigned hi = (unsigned)(b >> 32); memcpy(&P.LhF[k], &hi, 4); }
+    P.tabW_off = 10006 * 8;
+    double rcut = L / 2; P.rcut2 = rcut * rcut; P.dr = rcut / 9999.0; P.inv_dr = 1 / P.dr; P.half_inv_dr = 0.5 * P.inv_dr; P.rclamp2 = (P.Nmax + 3.5) * P.dr * (P.Nmax + 3.5) * P.dr; P.dt = 5e-3; P.wS[0] = 2 * P.dt / 3; P.wS[1] = 4 * P.dt / 3; P.wS[2] = P.dt / 3; P.cF = 4 * P.dt * P.dt * P.dt / 18;
     std::vector<double> tab(10006, 0.0), slices((size_t)nslices * 3 * P.NpS);
     for (int i = 0; i < 10002; ++i) { double r = (i + 1) * P.dr; tab[i] = 1.0 / (r * r * r + 0.1); }
     for (auto& v : slices) v = (rand() / (double)RAND_MAX - 0.5) * L;
@@ -71,7 +73,10 @@ int main(int argc, char** argv) {
         cudaEventRecord(a); kern<<<grid, block, smem>>>(d_sl, nslices, iters, d_out); cudaEventRecord(b); cudaEventSynchronize(b);
         float ms; cudaEventElapsedTime(&ms, a, b);
         double upd = (double)grid * warps_per_sm * iters;
-        printf("%-6s Np=%d slices=%d (%.0f MB) warps/SM=%d: %.1f M bead-updates/s  (%s)\n", name, Np, nslices, slices.size() * 8 / 1e6, warps_per_sm, upd / ms / 1e3, cudaGetErrorString(cudaGetLastError()));
+        std::vector<double> ho((size_t)grid * warps_per_sm);
+        cudaMemcpy(ho.data(), d_out, ho.size() * 8, cudaMemcpyDeviceToHost);
+        double cs = 0; for (double v : ho) cs += v;
+        printf("V%-2d %-6s Np=%d slices=%d (%.0f MB) warps/SM=%d: %.1f M bead-updates/s  checksum %.15e (%s)\n", PIGS_LOOPV, name, Np, nslices, slices.size() * 8 / 1e6, warps_per_sm, upd / ms / 1e3, cs, cudaGetErrorString(cudaGetLastError()));
     };
     run(k_loop<0>, "even"); run(k_loop<1>, "odd"); run(k_loop<2>, "end"); run(k_loop<3>, "mixed");
     return 0;

@@ -53,6 +53,52 @@ __global__ void thr_dfma(double* out, long long* cyc, int n) {
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// conversion throughput relative to DFMA: ops per thread per iteration = 8
+__global__ void thr_cvt_f2f(double* out, long long* cyc, int n) {
+    double a[8]; for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 1e-3 + k + 0.5;
+    float f[8];
+    __syncthreads();
+    long long t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f[k]) : "d"(a[k])); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += 1.0;
+    }
+    long long t1 = clock64();
+    double s = 0; for (int k = 0; k < 8; ++k) s += a[k] + f[k];
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void thr_rint_f64(double* out, long long* cyc, int n) {
+    double a[8]; for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 1e-3 + k + 0.5;
+    double f[8];
+    __syncthreads();
+    long long t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { asm volatile("cvt.rni.f64.f64 %0, %1;" : "=d"(f[k]) : "d"(a[k])); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += 1.0;
+    }
+    long long t1 = clock64();
+    double s = 0; for (int k = 0; k < 8; ++k) s += a[k] + f[k];
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void thr_dadd_only(double* out, long long* cyc, int n) {
+    double a[8]; for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 1e-3 + k + 0.5;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += 1.0;
+    }
+    long long t1 = clock64();
+    double s = 0; for (int k = 0; k < 8; ++k) s += a[k];
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 int main() {
     double* out; long long* cyc; cudaMalloc(&out, 1 << 24); cudaMalloc(&cyc, 4096);
     long long h[8]; int n = 4096;
@@ -69,6 +115,12 @@ int main() {
         thr_dfma<4><<<1, 32 * w>>>(out, cyc, n); cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost);
         double c4 = (double)h[0] / n;
         printf("warps/SM %2d: cycles per loop iter ILP1 %.2f  ILP2 %.2f  ILP4 %.2f   => DFMA warp-instr/clk/SM %.3f %.3f %.3f\n", w, c1, c2, c4, w / c1, 2 * w / c2, 4 * w / c4);
+    }
+    for (int w : {4, 16}) {
+        thr_dadd_only<<<1, 32 * w>>>(out, cyc, n); cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost); double c0 = (double)h[0] / n;
+        thr_cvt_f2f<<<1, 32 * w>>>(out, cyc, n); cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost); double c1 = (double)h[0] / n;
+        thr_rint_f64<<<1, 32 * w>>>(out, cyc, n); cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost); double c2 = (double)h[0] / n;
+        printf("warps/SM %2d: cycles per iter: 8 DADD %.1f | 8 DADD + 8 cvt.f32.f64 %.1f | 8 DADD + 8 cvt.rni.f64.f64 %.1f\n", w, c0, c1, c2);
     }
     cudaError_t e = cudaDeviceSynchronize(); printf("%s\n", cudaGetErrorString(e));
     return 0;

@@ -1,0 +1,49 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/ref_golden.json from the MACHINE-TRANSLATED REFERENCE (oracle/_ref/libpigs_ref.so, built
+by `make -C oracle ref` from /root/reference/*.f90 -- see oracle/f90toc/f90toc.py).  Run in the build container,
+where the reference sources live:
+
+    python tests/golden/make_ref_golden.py
+
+The vectors are outputs of the reference's own code (not of the hand-written oracle): leaf functions, the MT19937
+stream, and complete `./vpi < vpi.in` runs (e_vpi.out / et_vpi.out records, block by block).  Doubles are stored
+as C99 hex strings, so tests/test_ref_pin.py::test_oracle_matches_reference_goldens compares bit for bit, also
+where /root/reference does not exist (the GPU box)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import pigs_ref                                    # noqa: E402
+from tests.common import C1, C2, CW, CWX, CS, oracle_cfg       # noqa: E402
+
+
+def main():
+    G = dict(source="oracle/_ref/libpigs_ref.so = f90toc translation of /root/reference/*.f90, g++ -O2 -ffp-contract=off -fwrapv",
+             leaf=[], program=[])
+    r = pigs_ref.Ref(oracle_cfg(C2))
+    rng = np.random.default_rng(2026)
+    for x in rng.uniform(0.05, 4.5, 200):
+        G["leaf"].append(dict(f="potential", args=[float(x).hex()], want=r.L.ref_potential(float(x)).hex()))
+        for opt in (0, 1, 2):
+            G["leaf"].append(dict(f="logpsi", args=[opt, (1.2).hex(), float(x).hex()], want=r.L.ref_logpsi(opt, 1.2, float(x)).hex()))
+    r.sgrnd(1982)
+    G["stream"] = dict(cfg=oracle_cfg(CW), seed=1982, grnd=[r.grnd().hex() for _ in range(1300)],
+                       rangauss=[r.rangauss().hex() for _ in range(300)])
+    for name, cfg, Nblock, Nstep in (("CW", CW, 4, 25), ("CWX", CWX, 5, 25), ("CS", CS, 3, 20), ("C1", C1, 2, 10), ("C2", C2, 2, 2)):
+        c = oracle_cfg(cfg)
+        rr = pigs_ref.Ref(c, Nblock=Nblock, Nstep=Nstep)
+        G["program"].append(dict(name=name, cfg=c, Nblock=Nblock, Nstep=Nstep,
+                                 e_vpi=[[x.hex() for x in row] for row in rr.file("e_vpi.out").tolist()],
+                                 et_vpi=[[x.hex() for x in row] for row in rr.file("et_vpi.out").tolist()]))
+    out = os.path.join(ROOT, "tests", "golden", "ref_golden.json")
+    json.dump(G, open(out, "w"), indent=0)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
+if __name__ == "__main__":
+    main()
