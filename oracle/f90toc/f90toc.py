@@ -364,7 +364,8 @@ def parse_dims(s):
 
 
 class Translator:
-    def __init__(self, skip=(), io_unit_capture=True):
+    def __init__(self, skip=(), count=()):
+        self.count = set(count)          # procedures whose calls are counted (f90rt-free global `calls_<name>_`)
         self.modvars: dict[str, Sym] = {}
         self.procs: dict[str, Proc] = {}
         self.order: list[str] = []
@@ -936,6 +937,8 @@ class Translator:
 
     def translate_proc(self, q):
         L = [f"// {q.file}:{q.line}  {q.kind} {q.name}", self.proto(q) + " {"]
+        if q.name in self.count:
+            L.append(f"  ++calls_{self.cname(q.name)};")
         undef = []
         # statement functions
         for sf, (sargs, sexpr) in q.stmt_funcs.items():
@@ -1166,6 +1169,8 @@ class Translator:
         self.analyse()
         out = ["// GENERATED by oracle/f90toc/f90toc.py from the reference's Fortran sources -- do not edit, do not commit.",
                '#include "f90rt.h"', ""]
+        for n in sorted(self.count):
+            out.append(f"long long calls_{self.cname(n)} = 0;      // instrumentation: calls of {n}")
         # module / common variables
         for s in self.modvars.values():
             ct, n = CTYPE[s.ty], self.cname(s.name)
@@ -1230,8 +1235,9 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--files", default="global_mod.f90,bessel_skip,pbc_mod.f90,interpolate.f90,r8_gamma.f90,random_mod.f90,system_mod.f90,sample_mod.f90,vpi_mod.f90,vpi.f90")
     ap.add_argument("--skip", default="readparameters,readsystemparameters,mtsavef,mtgetf,checkpoint")
+    ap.add_argument("--count", default="updateaction", help="procedures whose calls are counted (the metric's unit)")
     a = ap.parse_args()
-    tr = Translator(skip=a.skip.split(","))
+    tr = Translator(skip=a.skip.split(","), count=[c for c in a.count.split(",") if c])
     for f in a.files.split(","):
         if f.endswith("_skip"):
             continue

@@ -69,6 +69,11 @@ int ref_run_program(const ref_params* p) {
     try { vpi_(); } catch (const std::exception& e) { std::fprintf(stderr, "ref_run_program: %s\n", e.what()); return -1; }
     return 0;
 }
+// UpdateAction calls so far (the metric's unit: one bead-update; counter injected by f90toc --count)
+long long ref_bead_updates(void) { return calls_updateaction_; }
+// queue one record for `read(unit,*)` statements (config_ini.in of crystal = .true.)
+void ref_queue_read(int unit, const double* v, int n) { f90rt::unit(unit).to_read.emplace_back(v, v + n); }
+void ref_clear_reads(int unit) { f90rt::unit(unit).to_read.clear(); f90rt::unit(unit).rpos = 0; }
 // records of one captured file, flattened row by row; returns the number of records, *ncol = widest record
 int ref_file(const char* name, double* buf, int cap, int* ncol) {
     auto& recs = f90rt::files().get(name);

@@ -623,14 +623,20 @@ PIGS_PRAGMA_UNROLL
 
 
 // ------------------------------------------------------------------ partner loop, second generation
-// Compile-time selection of the loop variants (bit mask, measured with scripts/loopbench.cu on B200):
-//   1  partner registers are reloaded in place right after their last use (no cur/nxt copy: -9 MOV, -6 registers)
-//   2  the moved particle excludes itself by a poisoned x coordinate (r^2 = inf -> zero tail) instead of two
-//      selects per position
-//   4  wrap count of the minimum image from a compare on the high word of d (2 FP64 slots per component, not 4)
-//   8  table reads through explicit ld.shared with a 32-bit base (no per-iteration window-base recomputation)
+// Compile-time selection of the loop variants (bit mask; measured in isolation with scripts/loopbench.cu on B200,
+// N = 256, mixed slice classes, 16 warps/SM, HBM-resident / L2-resident slices, M bead-updates/s):
+//   0   round-1 loop (cur/nxt register copy, per-position self mask)                      623 / 655
+//   1   partner registers reloaded IN PLACE right after their last use (no cur/nxt copy: -9 MOV, -6 registers);
+//       the moved particle excludes itself through a poisoned x coordinate (r^2 ~ 1e268 -> zero tail of the
+//       tables) instead of two selects per position                                         640 / 684
+//   32  + the cutoff acts on the table INDEX, off the critical path (sqrt of the unclamped r^2)     648 / 695   <- default
+//   16  + one Newton step instead of the three-term step (1e-12 in r): +0.7 %, not worth the digits   652 / 703
+//   4   wrap count of the minimum image from a compare on the high word of d: -12 FP64 slots, +10 ALU   635 / 678 (slower)
+//   8   table reads through explicit ld.shared with a 32-bit base: no change
+//   64  L1 prefetch two blocks ahead + L1-allocating loads: 593 / 639 (slower);  128 L1-allocating loads only: 648 / 706
+// Variants 1 and 32 give results bit-identical to variant 0.
 #ifndef PIGS_LOOPV
-#define PIGS_LOOPV 0
+#define PIGS_LOOPV 33
 #endif
 
 // d - L*q with q = -1, 0, +1 decided on the HIGH WORD of d: |d| > L/2 is judged with a resolution of 2^-20
