@@ -36,10 +36,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "MC bead-updates/sec, liquid He-4 N=256"
 UNIT = "bead-updates/s"
-WORKLOAD = "C3"
-CHAINS_PER_GPU = 2368          # 148 SMs x 16 chain groups
+CHAINS_PER_GPU = 2368          # C3 / C2: 148 SMs x 16 chain groups, the same on every GPU (weak scaling)
+C5_CHAINS = 4096               # C5 = BASELINE.json configs[4]: 4096 N=64 chains split over the GPUs (strong scaling)
+
+
+def metric_name(workload):
+    return {"C3": "MC bead-updates/sec, liquid He-4 N=256", "C2": "MC bead-updates/sec, liquid He-4 N=64",
+            "C5": "MC bead-updates/sec, 4096 independent He-4 N=64 chains"}[workload]
+
+
 MC_STEPS_PER_BLOCK = 4
 SEED = 20260101
 
@@ -53,96 +59,79 @@ def oracle_cfg(cfg):
     return c
 
 
-# ------------------------------------------------------------------ CPU oracle legs (the only oracle/ users here)
-def _oracle_worker(cfg, P0, xe0, seed, native, st):
-    from oracle.pigs_oracle import Oracle
-    o = Oracle(oracle_cfg(cfg), native=native)
-    o.fill_tables()
-    o.set_state(P0, xe0, 0, 0)
-    o.sgrnd(seed)
-    while True:
-        st["start"].wait()
-        if st["stop"]:
-            return
-        b, _, _, _ = o.run_block(st["nstep"])        # ctypes releases the GIL: the cores run concurrently
-        st["done"].append(sum(b["bead_updates"]))
-        st["end"].wait()
-
-
-class OraclePool:
-    """one independent reference chain per host core (the reference's only form of parallelism)"""
-
-    def __init__(self, cfg, cores, native=False):
-        from pathintegralgroundstate_b200.workloads import synthetic_paths
-        self.cores = cores
-        P, xe = synthetic_paths(cfg, cores, seed=SEED)
-        self.st = dict(start=threading.Barrier(cores + 1), end=threading.Barrier(cores + 1), stop=False, nstep=1, done=[])
-        self.threads = [threading.Thread(target=_oracle_worker, args=(cfg, P[i], xe[i], 1982 + i, native, self.st),
-                                         daemon=True) for i in range(cores)]
-        for t in self.threads:
-            t.start()
-
-    def step(self, nstep=1):
-        """every core advances its chain by nstep MC steps; returns (bead_updates, seconds)"""
-        self.st["nstep"] = nstep
-        self.st["done"].clear()
-        t0 = time.perf_counter()
-        self.st["start"].wait()
-        self.st["end"].wait()
-        dt = time.perf_counter() - t0
-        return sum(self.st["done"]), dt
-
-    def close(self):
-        self.st["stop"] = True
-        self.st["start"].wait()
-
-
+# ------------------------------------------------------------------ CPU legs (the only oracle/ users here)
 def host_cores():
     try:
-        return len(os.sched_getaffinity(0))
+        return sorted(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        return list(range(os.cpu_count() or 1))
 
 
-def cpu_baseline(cfg, budget_s=12.0):
-    cores = host_cores()
-    pool = OraclePool(cfg, cores)
-    pool.step(1)
-    n_tot, t_tot, nblk = 0, 0.0, 0
-    while t_tot < budget_s:
-        n, dt = pool.step(1)
-        n_tot += n
-        t_tot += dt
-        nblk += 1
-    pool.close()
-    return dict(value=n_tot / t_tot, unit=UNIT, cores=cores, kind="port",
-                sample=f"{cores} independent {WORKLOAD} chains (one per core, g++ -O2 C++ restatement of the Fortran "
-                       f"reference; gfortran unavailable in image), {nblk} MC steps each, {t_tot:.1f} s")
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_workers(workload, W, K, impl="ref", cores=None):
+    """one independent reference process per host core, pinned, own seed, same run.
+    Returns (bead-updates/s summed over the processes, seconds of the slowest, kind, n_processes)."""
+    import subprocess
+    cores = host_cores() if cores is None else cores
+    procs = [subprocess.Popen([sys.executable, "-m", "oracle.ref_worker", str(c), str(1982 + i), str(W), str(K), workload, impl],
+                              cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for i, c in enumerate(cores)]
+    upd, tmax, kind = 0, 0.0, "?"
+    for pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("reference worker failed: " + err[-800:])
+        d = json.loads(out.strip().splitlines()[-1])
+        upd += d["updates"]
+        tmax = max(tmax, d["seconds"])
+        kind = d["kind"]
+    return upd / tmax, tmax, kind, len(cores)
+
+
+def cpu_baseline(workload, W=1, K=8, reps=1, extras=True):
+    """the reference program (oracle/_ref: its Fortran machine-translated to C++, g++ -O2) on every host core;
+    beside it the hand-written port at -O2 and at -O3 -march=x86-64-v3"""
+    vals, secs = [], 0.0
+    for _ in range(reps):
+        v, t, kind, n = run_workers(workload, W, K, "ref")
+        vals.append(v)
+        secs += t
+    vals.sort()
+    out = dict(value=vals[len(vals) // 2], unit=UNIT, cores=n, seconds_per_rep=secs / reps,
+               kind="reference" if kind.startswith("reference") else "port", implementation=kind, cpu=cpu_model(),
+               sample=f"{n} pinned processes (one per host core, taskset-style affinity), each one independent {workload} chain "
+                      f"running the reference program for {K} MC steps after {W} warm-up steps; {reps} repetition(s), median; "
+                      f"{secs:.1f} s of CPU wall time",
+               spread=[vals[0], vals[-1]])
+    if extras:
+        out["value_port_O2"] = run_workers(workload, W, K, "port")[0]
+        out["value_port_native"] = run_workers(workload, W, K, "native")[0]
+    return out
 
 
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = host_cores()
-    pool = OraclePool(cfg, cores)
-    for _ in range(max(args.warmup, 1)):
-        pool.step(1)
-    n_tot, t_tot = 0, 0.0
-    for _ in range(args.steps):
-        n, dt = pool.step(1)
-        n_tot += n
-        t_tot += dt
-    pool.close()
-    v = n_tot / t_tot
-    sample = (f"{cores} independent {WORKLOAD} chains, one per host core, 1 MC step per bench step; C++ restatement of "
-              f"the Fortran reference (oracle/, g++ -O2): no Fortran compiler in this image")
+    t0 = time.perf_counter()
+    cb = cpu_baseline(args.workload, W=max(args.warmup, 1), K=args.steps, reps=3, extras=True)
+    v = cb["value"]
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric_name(args.workload), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * cb["seconds_per_rep"] / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong" if args.workload == "C5" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "Np": cfg["Np"], "Nb": cfg["Nb"], "chains": cores, "mc_steps_per_step": 1},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": args.workload, "Np": cfg["Np"], "Nb": cfg["Nb"], "chains": cb["cores"], "mc_steps_per_step": 1},
+        "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -182,17 +171,21 @@ def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
     from pathintegralgroundstate_b200 import PigsCuda, measure_fp64_peak
-    from pathintegralgroundstate_b200.multi_gpu import init_process_group, shard_chains, chain_seed, _CudaArray
+    from pathintegralgroundstate_b200.multi_gpu import init_process_group, shard_chains, _CudaArray
     from pathintegralgroundstate_b200.workloads import synthetic_paths, flops_per_bead_update
 
     rank, local, world = init_process_group("nccl")
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
-    n_chains = args.chains
-    first, _ = shard_chains(n_chains * world, rank, world)
+    strong = args.workload == "C5"
+    if strong:                                   # total work fixed: the 4096 chains are split over the ranks
+        first, n_chains = shard_chains(C5_CHAINS if args.chains == CHAINS_PER_GPU else args.chains, rank, world)
+    else:
+        n_chains = args.chains
+        first, _ = shard_chains(n_chains * world, rank, world)
 
-    sim = PigsCuda(cfg, n_chains=n_chains, rng="philox", seed=chain_seed(SEED, first), device=local)
+    sim = PigsCuda(cfg, n_chains=n_chains, rng="philox", seed=SEED, chain_offset=first, device=local, schedule=args.schedule)
     sim.fill_tables("hfdb")
     P, xe = synthetic_paths(cfg, n_chains, seed=SEED + 7919 * rank)
     # pinned host buffers of the chains' state (the e2e leg copies them every step)
@@ -298,7 +291,7 @@ def run_ours(args, cfg):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(WORKLOAD, {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -307,10 +300,10 @@ def run_ours(args, cfg):
                         "no FP64 entry); achieved = algorithmic flops 2(N-1)c+40 per bead-update (c=28/46/37 by slice "
                         "class) / CUDA-event time of the sweep kernel launches"}
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "Np": cfg["Np"], "Nb": cfg["Nb"], "chains_per_gpu": n_chains,
+        "config": {"workload": args.workload, "schedule": sim.schedule_name(), "Np": cfg["Np"], "Nb": cfg["Nb"], "chains_per_gpu": n_chains,
                    "mc_steps_per_step": nstep, "rng": "philox", "worm": "on (CWorm=0.5, Nobdm=10, swap)",
                    "estimators": "mixed+thermodynamic energy, g(r), S(k), OBDM",
                    "l2": f"inputs larger than L2: {state_bytes / 1e6:.0f} MB of paths per GPU stream from HBM",
@@ -323,7 +316,7 @@ def run_ours(args, cfg):
         "wall_ms_per_step": wall_ms / args.steps,
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(cfg)
+        out["cpu_baseline"] = cpu_baseline(args.workload)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -338,11 +331,14 @@ def main():
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
     ap.add_argument("--mc-steps", type=int, default=MC_STEPS_PER_BLOCK, help="driver MC steps per bench step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="C3", choices=["C3", "C2", "C5"],
+                    help="C3: the metric's configuration (N=256, worm on), weak scaling; C5: 4096 N=64 chains split over the GPUs")
+    ap.add_argument("--schedule", type=int, default=-1, help="-1 auto, 0 one warp per chain, 1 team (4 warps per chain)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                      # timing hygiene: at least 3 warm-up steps
     from pathintegralgroundstate_b200.workloads import config
-    cfg = config(WORKLOAD)
+    cfg = config("C2" if args.workload == "C5" else args.workload)
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

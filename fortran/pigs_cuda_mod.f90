@@ -32,6 +32,7 @@ type, bind(C) :: pigs_params
    integer(c_int32_t) :: n_chains, rng_mode
    integer(c_int64_t) :: seed
    integer(c_int32_t) :: device, threads_per_chain, table_mode, action
+   integer(c_int32_t) :: schedule = -1, chain_offset = 0, gpus = 1
 end type pigs_params
 
 ! struct pigs_block_result

@@ -89,6 +89,18 @@ typedef struct pigs_params {
     int32_t table_mode;                /* -1 = auto; 0 tables via L1/L2; 1 VTable in smem; 2 both in smem */
     int32_t action;                    /* 0 = Chin (the live propagator, global_mod.f90:33-46), 1 = primitive
                                           (the commented-out alternative, global_mod.f90:48,67) */
+    int32_t schedule;                  /* Philox mode only: -1 = auto, 0 = one thread group per chain walks the slice
+                                          windows of a pass one after the other, 1 = team: four warps per chain sweep
+                                          four disjoint windows concurrently (few chains per GPU).  MT19937 replay
+                                          always runs the reference's order (vpi.f90:412-439). */
+    int32_t chain_offset;              /* global index of this handle's chain 0 when the chains of one run are
+                                          sharded over several handles/GPUs: chain c draws the Philox stream of
+                                          global chain chain_offset + c (MT: sgrnd(seed + chain_offset + c)), so a
+                                          run is reproducible whatever the number of shards */
+    int32_t gpus;                      /* 0 or 1: one GPU (`device`).  G > 1: the handle shards the chains in
+                                          contiguous blocks over the GPUs device .. device+G-1 of this process and
+                                          sums the block accumulators itself at every block boundary (the
+                                          reference's reduction point, vpi.f90:477-520); no MPI, NCCL or torch needed */
 } pigs_params;
 
 /* Raw block sums, summed over chains, exactly the quantities the driver holds
@@ -153,6 +165,10 @@ int  pigs_sync(pigs_handle h);
 int  pigs_get_block(pigs_handle h, pigs_block_result* out, double* gr, double* Sk, double* nrho);
 /* same for one chain */
 int  pigs_get_block_chain(pigs_handle h, int chain, pigs_block_result* out, double* gr, double* Sk, double* nrho);
+/* The same for chains [chain0, chain0 + n) in one transfer: out[n], gr[n][Nbin], Sk[n][Nk][dim],
+ * nrho[n][Nbin][Npw+1] (any of them may be NULL).  Cross-chain statistics replace the reference's single-chain
+ * Var (sample_mod.f90:921-932). */
+int  pigs_get_block_chains(pigs_handle h, int chain0, int n, pigs_block_result* out, double* gr, double* Sk, double* nrho);
 /* device pointer + length (doubles) of the chain-summed accumulator vector of
  * the last block, laid out [12 energy sums | 24 counters as doubles | gr | Sk |
  * nrho]; for an in-place NCCL all-reduce by the caller (multi-GPU). */
@@ -164,6 +180,10 @@ int  pigs_last_block_ms(pigs_handle h, float* ms);
 /* the CUDA stream (cudaStream_t) the library launches on, and launch counters */
 int  pigs_stream(pigs_handle h, void** stream);
 int  pigs_launch_count(pigs_handle h, int64_t* n);
+/* the launch policy chosen for this handle (diagnostics): threads per chain group, chain groups per CTA, CTAs,
+ * team schedule (1: four window workers per chain), table placement (0 L1/L2, 1 VTable pairs in smem, 2 both in
+ * smem, 3 trap) */
+int  pigs_launch_plan(pigs_handle h, int* threads_per_chain, int* groups_per_cta, int* grid, int* team, int* table_mode);
 
 /* ---- unit API: one reference procedure per call, applied to EVERY chain's
  * device state with that chain's own random stream ---- */

@@ -69,6 +69,9 @@ def lib():
         L.ref_normalize_nr.argtypes = [D, D, I, P]
         L.ref_move.argtypes = [I, I, P, P, D, D, D, I, I, I, I, P, P, C.POINTER(I), C.POINTER(I)]
         L.ref_move.restype = I
+        L.ref_bead_updates.argtypes, L.ref_bead_updates.restype = [], C.c_longlong
+        L.ref_queue_read.argtypes = [I, P, I]
+        L.ref_clear_reads.argtypes = [I]
         _L = L
     return _L
 
@@ -88,8 +91,17 @@ class Ref:
                     sampling="bis", Lstag=2, Nlev=1, Nstag=5, Nblock=0, Nstep=1, Nbin=100, Nk=50, swapping=0, CWorm=0.0,
                     Nobdm=0, Npw=0, Nmax=10000, wf_table=1, v_table=1, Rm=1.2, a_ho=(1.0, 1.0, 1.0))
 
-    def __init__(self, cfg: dict, Nblock=0, Nstep=1):
+    def __init__(self, cfg: dict, Nblock=0, Nstep=1, lattice=None):
+        """lattice = (R[Np][dim], Lbox[dim]): run with crystal = .true.; the program then reads Np, Lbox, density and the
+        starting positions from config_ini.in (vpi.f90:101-107, vpi_mod.f90:218-228) -- served from memory here"""
         self.L = lib()
+        if lattice is not None:
+            R, Lb = np.asarray(lattice[0], float), np.asarray(lattice[1], float)
+            cfg = dict(cfg, crystal=1)
+            self.L.ref_clear_reads(2)
+            for rec in [[float(len(R))], list(Lb), [float(cfg["density"])]] + [list(x) for x in R]:
+                a = np.asarray(rec, float)
+                self.L.ref_queue_read(2, _dp(a), len(a))
         c = dict(self.DEFAULTS)
         c.update({k: v for k, v in cfg.items() if k in self.DEFAULTS})
         c["Nblock"], c["Nstep"] = Nblock, Nstep
@@ -113,6 +125,10 @@ class Ref:
         self.Lbox = Lb
         self.rcut, self.dr, self.rbin = [x.value for x in sc]
         self.dim, self.Np, self.Nb, self.Nmax = p.dim, p.Np, p.Nb, p.Nmax
+
+    def bead_updates(self):
+        """UpdateAction calls since the library was loaded (the metric's unit)"""
+        return int(self.L.ref_bead_updates())
 
     def file(self, name):
         """numeric records the program wrote to `name` (e_vpi.out, et_vpi.out, gr_vpi.out, sk_vpi.out, nr_vpi.out, fort.99)"""

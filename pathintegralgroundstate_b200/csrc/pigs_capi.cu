@@ -3,6 +3,7 @@
 #include "../../include/pigs_cuda.h"
 #include "pigs_launch.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -28,7 +29,7 @@ static int fail(int code, const std::string& m) { g_err = m; return code; }
 struct pigs_ctx {
     pigs_params hp;
     DevParams P;
-    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32, prefetch = 3, pfdist = 2;
+    int var = 0, mt = 0, T = 32, G = 1, grid = 1, block = 32, prefetch = 3, pfdist = 2, team = 0;
     size_t smem = 0;
     int nvec = 0;
     bool tables_set = false;
@@ -44,7 +45,30 @@ struct pigs_ctx {
     unsigned long long* d_pctr = nullptr;
     long long* d_cnt = nullptr;
     size_t stage_doubles = 0;
+    int* d_flag = nullptr;          // device flag: coordinates outside the box seen by an upload
+    // gpus > 1: this context owns no device memory; it shards the chains over one sub-context per GPU
+    std::vector<pigs_ctx*> sub;
+    std::vector<int> first;         // first[k] = global index of sub-context k's chain 0; first[gpus] = n_chains
 };
+// which sub-context holds global chain c (multi-GPU handles)
+static int shard_of(const pigs_ctx* h, int c) {
+    int k = 0;
+    while (k + 1 < (int)h->sub.size() && c >= h->first[k + 1]) ++k;
+    return k;
+}
+#define MULTI(h, expr) do { if ((h) && !(h)->sub.empty()) return (expr); } while (0)
+// route a per-chain call of a multi-GPU handle to the shard that owns the chain
+#define MULTI_CHAIN(h, c, call)                                                                                \
+    do {                                                                                                       \
+        if ((h) && !(h)->sub.empty()) {                                                                        \
+            if ((c) < 0 || (c) >= (h)->hp.n_chains) return fail(PIGS_E_ARG, "chain index out of range");      \
+            const int k_ = shard_of((h), (c));                                                                 \
+            pigs_ctx* s_ = (h)->sub[k_];                                                                       \
+            const int lc_ = (c) - (h)->first[k_];                                                              \
+            (void)lc_;                                                                                         \
+            return (call);                                                                                     \
+        }                                                                                                      \
+    } while (0)
 
 extern "C" const char* pigs_last_error(void) { return g_err.c_str(); }
 extern "C" int pigs_version(void) { return 100; }
@@ -59,13 +83,37 @@ static SweepArgs base_args(pigs_ctx* h) {
     while ((1 << A.tshift) < h->T) ++A.tshift;
     A.prefetch = h->prefetch;
     A.pfdist = h->pfdist;
+    A.team = h->team;
     return A;
+}
+// The kernels read their parameters from one __constant__ block per translation unit and device, uploaded on the
+// launching stream right before each launch.  A launch of ANOTHER handle on the same device must not overwrite the
+// block while an earlier kernel (e.g. an asynchronous block of the persistent sweep kernel, which re-reads it in
+// every phase) is still running: every (upload, launch) pair first waits for the previous handle's last launch.
+struct ConstGuard {
+    cudaEvent_t ev = nullptr;
+    const pigs_ctx* last = nullptr;
+};
+static ConstGuard g_guard[64];
+static int guard_enter(pigs_ctx* h) {          // g_launch_mutex held
+    ConstGuard& G = g_guard[h->hp.device & 63];
+    if (G.last && G.last != h && G.ev) CK(cudaStreamWaitEvent(h->st, G.ev, 0));
+    return PIGS_OK;
+}
+static int guard_leave(pigs_ctx* h) {
+    ConstGuard& G = g_guard[h->hp.device & 63];
+    if (!G.ev) CK(cudaEventCreateWithFlags(&G.ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(G.ev, h->st));
+    G.last = h;
+    return PIGS_OK;
 }
 static int launch(pigs_ctx* h, const SweepArgs& A) {
     std::lock_guard<std::mutex> lk(g_launch_mutex);
+    int rc = guard_enter(h);
+    if (rc) return rc;
     CK(launch_sweep(h->mt, h->var, h->P, A, h->grid, h->block, h->smem, h->st));
     h->launches += 1;
-    return PIGS_OK;
+    return guard_leave(h);
 }
 
 // launch policy: threads per chain T, chain groups per CTA G, table placement.
@@ -76,6 +124,23 @@ static int plan(pigs_ctx* h) {
     const int nsm = prop.multiProcessorCount;
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     int T = p.threads_per_chain;
+    // Team mode (Philox only): T = 128, the four warps of a chain group sweep four disjoint slice windows of the
+    // chain at once (win_sweep, pigs_sweep.cuh).  Chosen when one warp per chain would leave most of the GPU idle
+    // (at most 4 chains per SM) and the path is long enough for a head, a tail and a middle window side by side.
+    int team = 0;
+    if (!h->mt && (T == 0 || T == 128)) {
+        const int Lend = p.sampling ? (1 << (p.Nlev < 2 ? 2 : p.Nlev)) : p.Lstag;
+        const int Lm = p.sampling ? (1 << p.Nlev) : p.Lstag;
+        const bool fits = p.Np >= 4 && Lm >= 2 && (2 * p.Nb - 2 * Lend + 1) >= (Lm - 1);
+        int want_team = p.schedule;
+        const char* e = getenv("PIGS_SCHEDULE");      // tuning knob
+        if (e) want_team = atoi(e);
+        if (want_team < 0) want_team = (p.n_chains <= 4 * nsm) ? 1 : 0;
+        if (want_team == 1 && !fits && p.schedule == 1) return fail(PIGS_E_ARG, "schedule = 1 (team): the path is too short for concurrent windows");
+        team = (want_team == 1 && fits) ? 1 : 0;
+        if (team) T = 128;
+    } else if (p.schedule == 1) return fail(PIGS_E_ARG, "schedule = 1 (team) needs the Philox stream and threads_per_chain 0 or 128");
+    h->team = team;
     if (T == 0) {
         // fill ~32 warps per SM: few chains -> wide groups, many chains -> one warp each
         int maxt0 = 1024;
@@ -89,7 +154,7 @@ static int plan(pigs_ctx* h) {
         while (T * 2 <= want && T < tcap) T *= 2;
     }
     if (T != 32 && T != 64 && T != 128 && T != 256 && T != 512) return fail(PIGS_E_ARG, "threads_per_chain must be 0,32,64,128,256,512");
-    const size_t gbytes = (grp_smem_bytes(h->P.S, h->P.Np, T / 32) + 15) & ~(size_t)15;
+    const size_t gbytes = ((grp_smem_bytes(h->P.S, h->P.Np, T / 32) + 15) & ~(size_t)15) * (team ? 4 : 1);      // team: one block per window worker
     const size_t tabbytes = (size_t)tab_len(p.Nmax) * sizeof(double);
     const size_t pairbytes = (size_t)(tab_len(p.Nmax) - 1) * 2 * sizeof(double);      // table_mode 1: {F(i),F(i+1)} pairs
     int maxt = 1024;
@@ -143,36 +208,9 @@ static int plan(pigs_ctx* h) {
     return PIGS_OK;
 }
 
-extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
-    if (!p || !out) return fail(PIGS_E_ARG, "null argument");
-    *out = nullptr;
-    if (p->dim < 1 || p->dim > 3) return fail(PIGS_E_ARG, "dim must be 1..3");
-    if (2 * p->Nb + 1 > MAXS) return fail(PIGS_E_ARG, "Nb too large (2*Nb+1 must not exceed 132)");
-    if (p->Np < 2 || p->Nb < 1 || p->Nmax < 4 || p->n_chains < 1) return fail(PIGS_E_ARG, "Np>=2, Nb>=1, Nmax>=4, n_chains>=1 required");
-    if (p->Nbin < 1 || p->Nk < 0 || p->Npw < 0) return fail(PIGS_E_ARG, "bad Nbin/Nk/Npw");
-    if (p->sampling != 0 && p->sampling != 1) return fail(PIGS_E_ARG, "sampling must be 0 ('sta') or 1 ('bis')");
-    if (p->CMFreq < 1 || p->Nstag < 0 || p->Nobdm < 0) return fail(PIGS_E_ARG, "bad CMFreq/Nstag/Nobdm");
-    // constraints implied by the reference's index arithmetic (SURVEY Appendix C)
-    if (p->sampling == 1) {
-        int lv = p->Nlev < 2 ? 2 : p->Nlev;     // head/tail bisection draw Nlev' in [2, max(2,Nlev)]
-        if ((1 << lv) > 2 * p->Nb) return fail(PIGS_E_ARG, "2**Nlev must not exceed 2*Nb");
-    } else if (p->Lstag < 2 || p->Lstag > 2 * p->Nb) return fail(PIGS_E_ARG, "2 <= Lstag <= 2*Nb required");
-    if ((p->Nobdm > 0 || p->CWorm > 0 || p->swapping) && (p->Lstag < 2 || p->Lstag > p->Nb))
-        return fail(PIGS_E_ARG, "worm moves need 2 <= Lstag <= Nb");
-    if (p->Lstag < 2) return fail(PIGS_E_ARG, "Lstag >= 2 required (OpenChain is attempted even when CWorm = 0)");
-    if (p->Lstag > p->Nb) return fail(PIGS_E_ARG, "Lstag <= Nb required (OpenChain is attempted even when CWorm = 0)");
-    if (p->rng_mode != PIGS_RNG_PHILOX && p->rng_mode != PIGS_RNG_MT_REPLAY) return fail(PIGS_E_ARG, "bad rng_mode");
-    if (p->action != 0 && p->action != 1) return fail(PIGS_E_ARG, "action must be 0 (Chin) or 1 (primitive)");
-    if (!(p->dt > 0) || !(p->dr > 0) || !(p->rcut > 0)) return fail(PIGS_E_ARG, "dt, dr, rcut must be positive");
-
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
-        return fail(PIGS_E_CUDA, std::string("no CUDA device: libpigs_cuda has no CPU fallback (") + cudaGetErrorString(e) + ")");
-    if (p->device < 0 || p->device >= ndev) return fail(PIGS_E_ARG, "bad device ordinal");
+// everything a single-GPU context owns; on any failure the caller destroys the half-built context (no leak)
+static int init_single(pigs_ctx* h, const pigs_params* p) {
     CK(cudaSetDevice(p->device));
-
-    pigs_ctx* h = new pigs_ctx();
     h->hp = *p;
     h->mt = p->rng_mode == PIGS_RNG_MT_REPLAY ? 1 : 0;
     {
@@ -188,6 +226,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     P.Nmax = p->Nmax; P.Nbin = p->Nbin; P.Nk = p->Nk; P.Npw = p->Npw;
     P.trap = p->trap != 0; P.sampling = p->sampling; P.Lstag = p->Lstag; P.Nlev = p->Nlev; P.Nstag = p->Nstag;
     P.Nobdm = p->Nobdm; P.swapping = p->swapping != 0; P.CMFreq = p->CMFreq; P.n_chains = p->n_chains;
+    P.chain_offset = p->chain_offset;
     for (int k = 0; k < 3; ++k) {
         bool used = k < p->dim && !p->trap;
         P.L[k] = used ? p->Lbox[k] : 1e300;
@@ -235,7 +274,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     ALLOC(h->d_logwf, tab_len(p->Nmax)); ALLOC(h->d_vtab, tab_len(p->Nmax));      // zero tail: TAB_PAD
     ALLOC(h->d_path, nc * P.chain_stride); ALLOC(h->d_xend, nc * 6);
     ALLOC(h->d_istate, nc * IS_N); ALLOC(h->d_cyc, nc * P.Np); ALLOC(h->d_hist, nc * P.Np);
-    ALLOC(h->d_mt, nc * 624); ALLOC(h->d_pctr, nc); ALLOC(h->d_acc, nc * P.nacc); ALLOC(h->d_cnt, nc * NCNT);
+    ALLOC(h->d_mt, nc * 624); ALLOC(h->d_pctr, nc * PCS); ALLOC(h->d_acc, nc * P.nacc); ALLOC(h->d_cnt, nc * NCNT);
     ALLOC(h->d_vec, h->nvec); ALLOC(h->d_iout, nc * 2);
 #undef ALLOC
     CK(cudaMemset(h->d_path, 0, sizeof(double) * nc * P.chain_stride));
@@ -243,7 +282,7 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     CK(cudaMemset(h->d_istate, 0, sizeof(int) * nc * IS_N));
     CK(cudaMemset(h->d_cyc, 0, sizeof(int) * nc * P.Np));
     CK(cudaMemset(h->d_hist, 0, sizeof(int) * nc * P.Np));
-    CK(cudaMemset(h->d_pctr, 0, sizeof(unsigned long long) * nc));
+    CK(cudaMemset(h->d_pctr, 0, sizeof(unsigned long long) * nc * PCS));
     CK(cudaMemset(h->d_acc, 0, sizeof(double) * nc * P.nacc));
     CK(cudaMemset(h->d_cnt, 0, sizeof(long long) * nc * NCNT));
     CK(cudaMemset(h->d_logwf, 0, sizeof(double) * tab_len(p->Nmax)));
@@ -252,18 +291,94 @@ extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
     P.cyc = h->d_cyc; P.hist = h->d_hist; P.mt = h->d_mt; P.pctr = h->d_pctr; P.acc = h->d_acc; P.cnt = h->d_cnt;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+    CK(cudaMalloc((void**)&h->d_flag, sizeof(int)));
+    CK(cudaMemset(h->d_flag, 0, sizeof(int)));
     int rc = plan(h);
-    if (rc != PIGS_OK) { pigs_destroy(h); return rc; }
+    if (rc != PIGS_OK) return rc;
     // sgrnd(seed + chain) for every chain (random_mod.f90:5-31)
+    return pigs_sgrnd(h, -1, (int32_t)p->seed);
+}
+
+// gpus > 1: one sub-context per device device, device+1, ...; chains sharded in contiguous blocks, every shard
+// knows the global index of its first chain (chain_offset), so each chain draws the same stream as in a 1-GPU run
+static int create_multi(const pigs_params* p, int ndev, pigs_handle* out) {
+    const int G = p->gpus;
+    const bool same = getenv("PIGS_MULTI_SAME_DEVICE") != nullptr;      // testing aid: all shards on one device
+    if (!same && p->device + G > ndev) return fail(PIGS_E_ARG, "gpus exceeds the devices available from `device` on");
+    if (G > p->n_chains) return fail(PIGS_E_ARG, "more GPUs than chains: a single chain does not shard (replicas only)");
+    pigs_ctx* h = new pigs_ctx();
+    h->hp = *p;
+    h->first.resize(G + 1);
+    for (int k = 0; k <= G; ++k) h->first[k] = (int)((long long)p->n_chains * k / G);
+    for (int k = 0; k < G; ++k) {
+        pigs_params q = *p;
+        q.gpus = 1;
+        q.device = same ? p->device : p->device + k;
+        q.n_chains = h->first[k + 1] - h->first[k];
+        q.chain_offset = p->chain_offset + h->first[k];
+        pigs_handle sk = nullptr;
+        int rc = pigs_create(&q, &sk);
+        if (rc != PIGS_OK) { pigs_destroy(h); return rc; }
+        h->sub.push_back(sk);
+    }
+    h->P = h->sub[0]->P;
+    h->nvec = h->sub[0]->nvec;
     *out = h;
-    rc = pigs_sgrnd(h, -1, (int32_t)p->seed);
-    if (rc != PIGS_OK) { *out = nullptr; pigs_destroy(h); return rc; }
+    return PIGS_OK;
+}
+
+extern "C" int pigs_create(const pigs_params* p, pigs_handle* out) {
+    if (!p || !out) return fail(PIGS_E_ARG, "null argument");
+    *out = nullptr;
+    if (p->dim < 1 || p->dim > 3) return fail(PIGS_E_ARG, "dim must be 1..3");
+    if (2 * p->Nb + 1 > MAXS) return fail(PIGS_E_ARG, "Nb too large (2*Nb+1 must not exceed 132)");
+    if (p->Np < 2 || p->Nb < 1 || p->Nmax < 4 || p->n_chains < 1) return fail(PIGS_E_ARG, "Np>=2, Nb>=1, Nmax>=4, n_chains>=1 required");
+    if (p->Nbin < 1 || p->Nk < 0 || p->Npw < 0) return fail(PIGS_E_ARG, "bad Nbin/Nk/Npw");
+    if (p->sampling != 0 && p->sampling != 1) return fail(PIGS_E_ARG, "sampling must be 0 ('sta') or 1 ('bis')");
+    if (p->CMFreq < 1 || p->Nstag < 0 || p->Nobdm < 0) return fail(PIGS_E_ARG, "bad CMFreq/Nstag/Nobdm");
+    // constraints implied by the reference's index arithmetic (SURVEY Appendix C)
+    if (p->sampling == 1) {
+        int lv = p->Nlev < 2 ? 2 : p->Nlev;     // head/tail bisection draw Nlev' in [2, max(2,Nlev)]
+        if ((1 << lv) > 2 * p->Nb) return fail(PIGS_E_ARG, "2**Nlev must not exceed 2*Nb");
+    } else if (p->Lstag < 2 || p->Lstag > 2 * p->Nb) return fail(PIGS_E_ARG, "2 <= Lstag <= 2*Nb required");
+    if ((p->Nobdm > 0 || p->CWorm > 0 || p->swapping) && (p->Lstag < 2 || p->Lstag > p->Nb))
+        return fail(PIGS_E_ARG, "worm moves need 2 <= Lstag <= Nb");
+    if (p->Lstag < 2) return fail(PIGS_E_ARG, "Lstag >= 2 required (OpenChain is attempted even when CWorm = 0)");
+    if (p->Lstag > p->Nb) return fail(PIGS_E_ARG, "Lstag <= Nb required (OpenChain is attempted even when CWorm = 0)");
+    if (p->rng_mode != PIGS_RNG_PHILOX && p->rng_mode != PIGS_RNG_MT_REPLAY) return fail(PIGS_E_ARG, "bad rng_mode");
+    if (p->action != 0 && p->action != 1) return fail(PIGS_E_ARG, "action must be 0 (Chin) or 1 (primitive)");
+    if (p->schedule < -1 || p->schedule > 1) return fail(PIGS_E_ARG, "schedule must be -1 (auto), 0 or 1 (team)");
+    if (p->chain_offset < 0) return fail(PIGS_E_ARG, "chain_offset < 0");
+    if (!(p->dt > 0) || !(p->dr > 0) || !(p->rcut > 0)) return fail(PIGS_E_ARG, "dt, dr, rcut must be positive");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PIGS_E_CUDA, std::string("no CUDA device: libpigs_cuda has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    if (p->device < 0 || p->device >= ndev) return fail(PIGS_E_ARG, "bad device ordinal");
+    if (p->gpus < 0) return fail(PIGS_E_ARG, "gpus < 0");
+    if (p->gpus > 1) return create_multi(p, ndev, out);
+    pigs_ctx* h = new pigs_ctx();
+    const int rc = init_single(h, p);
+    if (rc != PIGS_OK) { pigs_destroy(h); return rc; }
+    *out = h;
     return PIGS_OK;
 }
 
 extern "C" int pigs_destroy(pigs_handle h) {
     if (!h) return PIGS_OK;
+    if (!h->sub.empty() || !h->first.empty()) {
+        for (pigs_ctx* s : h->sub) pigs_destroy(s);
+        delete h;
+        return PIGS_OK;
+    }
     cudaSetDevice(h->hp.device);
+    {   // nothing of this handle may still be reading the constant block when the next handle uploads
+        std::lock_guard<std::mutex> lk(g_launch_mutex);
+        ConstGuard& G = g_guard[h->hp.device & 63];
+        if (G.last == h) { if (h->st) cudaStreamSynchronize(h->st); G.last = nullptr; }
+    }
+    cudaFree(h->d_flag);
     cudaFree(h->d_logwf); cudaFree(h->d_vtab); cudaFree(h->d_path); cudaFree(h->d_xend); cudaFree(h->d_istate);
     cudaFree(h->d_cyc); cudaFree(h->d_hist); cudaFree(h->d_mt); cudaFree(h->d_pctr); cudaFree(h->d_acc);
     cudaFree(h->d_cnt); cudaFree(h->d_vec); cudaFree(h->d_iout); cudaFree(h->d_stage);
@@ -287,6 +402,11 @@ static int ensure_stage(pigs_ctx* h, size_t doubles) {
 }
 
 extern "C" int pigs_set_tables(pigs_handle h, const double* LogWF, const double* VTable) {
+    if (h && !h->sub.empty()) {
+        for (pigs_ctx* s : h->sub) { int rc = pigs_set_tables(s, LogWF, VTable); if (rc) return rc; }
+        h->tables_set = true;
+        return PIGS_OK;
+    }
     NEED(h);
     if (!LogWF || !VTable) return fail(PIGS_E_ARG, "null table");
     size_t n = sizeof(double) * (h->hp.Nmax + 2);
@@ -304,8 +424,14 @@ static int put_paths(pigs_ctx* h, int chain0, int nchain, const double* Path) {
     int rc = ensure_stage(h, per * nchain);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->d_stage, Path, per * nchain * sizeof(double), cudaMemcpyHostToDevice, h->st));
-    CK(launch_aos_to_soa(P, h->d_stage, h->d_path + (size_t)chain0 * P.chain_stride, nchain, h->st));
+    CK(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->st));
+    CK(launch_aos_to_soa(P, h->d_stage, h->d_path + (size_t)chain0 * P.chain_stride, nchain, h->st, h->d_flag));
     h->launches += 1;
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (bad) return fail(PIGS_E_ARG, "Path has coordinates outside the periodic box [-L/2, L/2] (or NaN): wrap them first "
+                                     "(BoundaryConditions, pbc_mod.f90:11-25) -- the action takes one periodic image per component");
     return PIGS_OK;
 }
 static int get_paths(pigs_ctx* h, int chain0, int nchain, double* Path) {
@@ -351,6 +477,7 @@ static int get_scalars(pigs_ctx* h, int chain0, int nchain, double* xend, int32_
 }
 
 extern "C" int pigs_set_state(pigs_handle h, int chain, const double* Path, const double* xend, int isopen, int iworm) {
+    MULTI_CHAIN(h, chain, pigs_set_state(s_, lc_, Path, xend, isopen, iworm));
     NEED(h); NEED_CHAIN(h, chain);
     if (!Path || !xend) return fail(PIGS_E_ARG, "null state");
     int rc = put_paths(h, chain, 1, Path);
@@ -359,6 +486,7 @@ extern "C" int pigs_set_state(pigs_handle h, int chain, const double* Path, cons
     return put_scalars(h, chain, 1, xend, &io, &iw);
 }
 extern "C" int pigs_get_state(pigs_handle h, int chain, double* Path, double* xend, int* isopen, int* iworm) {
+    MULTI_CHAIN(h, chain, pigs_get_state(s_, lc_, Path, xend, isopen, iworm));
     NEED(h); NEED_CHAIN(h, chain);
     if (Path) { int rc = get_paths(h, chain, 1, Path); if (rc) return rc; }
     int32_t io = 0, iw = 0;
@@ -368,6 +496,16 @@ extern "C" int pigs_get_state(pigs_handle h, int chain, double* Path, double* xe
     return rc;
 }
 extern "C" int pigs_set_state_all(pigs_handle h, const double* Path, const double* xend, const int32_t* isopen, const int32_t* iworm) {
+    if (h && !h->sub.empty()) {
+        if (!Path || !xend || !isopen || !iworm) return fail(PIGS_E_ARG, "null state");
+        const size_t per = (size_t)h->P.S * h->P.Np * h->P.dim;
+        for (size_t k = 0; k < h->sub.size(); ++k) {
+            const size_t f = (size_t)h->first[k];
+            int rc = pigs_set_state_all(h->sub[k], Path + f * per, xend + f * 2 * h->P.dim, isopen + f, iworm + f);
+            if (rc) return rc;
+        }
+        return PIGS_OK;
+    }
     NEED(h);
     if (!Path || !xend || !isopen || !iworm) return fail(PIGS_E_ARG, "null state");
     int rc = put_paths(h, 0, h->hp.n_chains, Path);
@@ -375,12 +513,23 @@ extern "C" int pigs_set_state_all(pigs_handle h, const double* Path, const doubl
     return put_scalars(h, 0, h->hp.n_chains, xend, isopen, iworm);
 }
 extern "C" int pigs_get_state_all(pigs_handle h, double* Path, double* xend, int32_t* isopen, int32_t* iworm) {
+    if (h && !h->sub.empty()) {
+        const size_t per = (size_t)h->P.S * h->P.Np * h->P.dim;
+        for (size_t k = 0; k < h->sub.size(); ++k) {
+            const size_t f = (size_t)h->first[k];
+            int rc = pigs_get_state_all(h->sub[k], Path ? Path + f * per : nullptr, xend ? xend + f * 2 * h->P.dim : nullptr,
+                                        isopen ? isopen + f : nullptr, iworm ? iworm + f : nullptr);
+            if (rc) return rc;
+        }
+        return PIGS_OK;
+    }
     NEED(h);
     if (Path) { int rc = get_paths(h, 0, h->hp.n_chains, Path); if (rc) return rc; }
     return get_scalars(h, 0, h->hp.n_chains, xend, isopen, iworm);
 }
 
 extern "C" int pigs_get_perm(pigs_handle h, int chain, int* iperm, int32_t* cycle, int32_t* hist, int* new_pc, int* end_pc) {
+    MULTI_CHAIN(h, chain, pigs_get_perm(s_, lc_, iperm, cycle, hist, new_pc, end_pc));
     NEED(h); NEED_CHAIN(h, chain);
     int ist[IS_N];
     CK(cudaMemcpyAsync(ist, h->d_istate + (size_t)chain * IS_N, sizeof ist, cudaMemcpyDeviceToHost, h->st));
@@ -393,6 +542,7 @@ extern "C" int pigs_get_perm(pigs_handle h, int chain, int* iperm, int32_t* cycl
     return PIGS_OK;
 }
 extern "C" int pigs_set_perm(pigs_handle h, int chain, int iperm, const int32_t* cycle, const int32_t* hist, int new_pc, int end_pc) {
+    MULTI_CHAIN(h, chain, pigs_set_perm(s_, lc_, iperm, cycle, hist, new_pc, end_pc));
     NEED(h); NEED_CHAIN(h, chain);
     int ist[IS_N];
     CK(cudaMemcpyAsync(ist, h->d_istate + (size_t)chain * IS_N, sizeof ist, cudaMemcpyDeviceToHost, h->st));
@@ -408,6 +558,10 @@ extern "C" int pigs_set_perm(pigs_handle h, int chain, int iperm, const int32_t*
 
 // ---- random streams ----------------------------------------------------------------------------
 extern "C" int pigs_sgrnd(pigs_handle h, int chain, int32_t seed) {
+    if (h && !h->sub.empty()) {
+        if (chain < 0) { for (pigs_ctx* s : h->sub) { int rc = pigs_sgrnd(s, -1, seed); if (rc) return rc; } return PIGS_OK; }
+        MULTI_CHAIN(h, chain, pigs_sgrnd(s_, lc_, seed));
+    }
     NEED(h);
     if (chain >= h->hp.n_chains) return fail(PIGS_E_ARG, "chain index out of range");
     SweepArgs A = base_args(h);
@@ -418,6 +572,7 @@ extern "C" int pigs_sgrnd(pigs_handle h, int chain, int32_t seed) {
     return PIGS_OK;
 }
 extern "C" int pigs_get_mt(pigs_handle h, int chain, uint32_t* mt624, int32_t* mti) {
+    MULTI_CHAIN(h, chain, pigs_get_mt(s_, lc_, mt624, mti));
     NEED(h); NEED_CHAIN(h, chain);
     int v = 0;
     if (mt624) CK(cudaMemcpyAsync(mt624, h->d_mt + (size_t)chain * 624, 624 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->st));
@@ -427,6 +582,7 @@ extern "C" int pigs_get_mt(pigs_handle h, int chain, uint32_t* mt624, int32_t* m
     return PIGS_OK;
 }
 extern "C" int pigs_set_mt(pigs_handle h, int chain, const uint32_t* mt624, int32_t mti) {
+    MULTI_CHAIN(h, chain, pigs_set_mt(s_, lc_, mt624, mti));
     NEED(h); NEED_CHAIN(h, chain);
     if (!mt624) return fail(PIGS_E_ARG, "null mt state");
     if (mti < 0 || mti > 625) return fail(PIGS_E_ARG, "mti must be in 0..625");
@@ -449,11 +605,15 @@ static int draws(pigs_ctx* h, int op, int chain, int n, double* out) {
     CK(cudaStreamSynchronize(h->st));
     return PIGS_OK;
 }
-extern "C" int pigs_grnd(pigs_handle h, int chain, int n, double* out) { NEED(h); NEED_CHAIN(h, chain); return draws(h, OP_UNIFORM, chain, n, out); }
-extern "C" int pigs_rangauss(pigs_handle h, int chain, int n, double* out) { NEED(h); NEED_CHAIN(h, chain); return draws(h, OP_GAUSS, chain, n, out); }
+extern "C" int pigs_grnd(pigs_handle h, int chain, int n, double* out) { MULTI_CHAIN(h, chain, pigs_grnd(s_, lc_, n, out)); NEED(h); NEED_CHAIN(h, chain); return draws(h, OP_UNIFORM, chain, n, out); }
+extern "C" int pigs_rangauss(pigs_handle h, int chain, int n, double* out) { MULTI_CHAIN(h, chain, pigs_rangauss(s_, lc_, n, out)); NEED(h); NEED_CHAIN(h, chain); return draws(h, OP_GAUSS, chain, n, out); }
 
 // ---- production path ---------------------------------------------------------------------------
 extern "C" int pigs_run_block_async(pigs_handle h, int Nstep) {
+    if (h && !h->sub.empty()) {          // every GPU gets its launch before anybody waits
+        for (pigs_ctx* s : h->sub) { int rc = pigs_run_block_async(s, Nstep); if (rc) return rc; }
+        return PIGS_OK;
+    }
     NEED(h);
     if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
     if (Nstep < 0) return fail(PIGS_E_ARG, "Nstep < 0");
@@ -469,11 +629,29 @@ extern "C" int pigs_run_block_async(pigs_handle h, int Nstep) {
     return PIGS_OK;
 }
 extern "C" int pigs_sync(pigs_handle h) {
+    if (h && !h->sub.empty()) {
+        for (pigs_ctx* s : h->sub) { int rc = pigs_sync(s); if (rc) return rc; }
+        return PIGS_OK;
+    }
     NEED(h);
     CK(cudaStreamSynchronize(h->st));
     return PIGS_OK;
 }
 extern "C" int pigs_run_block(pigs_handle h, int Nstep) {
+    if (h && !h->sub.empty()) {
+        int rc = pigs_run_block_async(h, Nstep);
+        if (rc) return rc;
+        h->last_ms = 0.f;
+        for (pigs_ctx* s : h->sub) {
+            float ms = 0.f;
+            rc = pigs_sync(s);
+            if (rc) return rc;
+            rc = pigs_last_block_ms(s, &ms);
+            if (rc) return rc;
+            if (ms > h->last_ms) h->last_ms = ms;      // the block ends when the slowest GPU ends
+        }
+        return PIGS_OK;
+    }
     int rc = pigs_run_block_async(h, Nstep);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->st));
@@ -481,14 +659,37 @@ extern "C" int pigs_run_block(pigs_handle h, int Nstep) {
     return PIGS_OK;
 }
 extern "C" int pigs_last_block_ms(pigs_handle h, float* ms) {
+    if (h && !h->sub.empty()) {
+        float m = 0.f;
+        for (pigs_ctx* s : h->sub) { float x = 0.f; int rc = pigs_last_block_ms(s, &x); if (rc) return rc; if (x > m) m = x; }
+        if (ms) *ms = m;
+        return PIGS_OK;
+    }
     NEED(h);
     CK(cudaEventSynchronize(h->ev1));
     CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     if (ms) *ms = h->last_ms;
     return PIGS_OK;
 }
-extern "C" int pigs_stream(pigs_handle h, void** stream) { NEED(h); if (stream) *stream = (void*)h->st; return PIGS_OK; }
-extern "C" int pigs_launch_count(pigs_handle h, int64_t* n) { NEED(h); if (n) *n = h->launches; return PIGS_OK; }
+extern "C" int pigs_launch_plan(pigs_handle h, int* threads_per_chain, int* groups_per_cta, int* grid, int* team, int* table_mode) {
+    MULTI(h, pigs_launch_plan(h->sub[0], threads_per_chain, groups_per_cta, grid, team, table_mode));
+    NEED(h);
+    if (threads_per_chain) *threads_per_chain = h->T;
+    if (groups_per_cta) *groups_per_cta = h->G;
+    if (grid) *grid = h->grid;
+    if (team) *team = h->team;
+    if (table_mode) *table_mode = h->var;
+    return PIGS_OK;
+}
+extern "C" int pigs_stream(pigs_handle h, void** stream) { MULTI(h, pigs_stream(h->sub[0], stream)); NEED(h); if (stream) *stream = (void*)h->st; return PIGS_OK; }
+extern "C" int pigs_launch_count(pigs_handle h, int64_t* n) {
+    if (h && !h->sub.empty()) {
+        int64_t t = 0;
+        for (pigs_ctx* s : h->sub) { int64_t x = 0; pigs_launch_count(s, &x); t += x; }
+        if (n) *n = t;
+        return PIGS_OK;
+    }
+    NEED(h); if (n) *n = h->launches; return PIGS_OK; }
 
 static void unpack(const pigs_ctx* h, const double* vec, pigs_block_result* out, double* gr, double* Sk, double* nrho) {
     const DevParams& P = h->P;
@@ -504,6 +705,19 @@ static void unpack(const pigs_ctx* h, const double* vec, pigs_block_result* out,
     if (nrho) std::memcpy(nrho, hst + P.Nbin + P.dim * P.Nk, sizeof(double) * P.Nbin * (P.Npw + 1));
 }
 extern "C" int pigs_get_block(pigs_handle h, pigs_block_result* out, double* gr, double* Sk, double* nrho) {
+    if (h && !h->sub.empty()) {
+        // the block-boundary reduction over GPUs (the reference's reduction point, vpi.f90:477-520): each GPU has
+        // already summed its chains in a fixed order (k_reduce_block); the ~3 KB vectors are added here in GPU order
+        std::vector<double> tot((size_t)h->nvec, 0.0), v((size_t)h->nvec);
+        for (pigs_ctx* s : h->sub) {
+            CK(cudaSetDevice(s->hp.device));
+            CK(cudaMemcpyAsync(v.data(), s->d_vec, sizeof(double) * h->nvec, cudaMemcpyDeviceToHost, s->st));
+            CK(cudaStreamSynchronize(s->st));
+            for (int i = 0; i < h->nvec; ++i) tot[i] += v[i];
+        }
+        unpack(h->sub[0], tot.data(), out, gr, Sk, nrho);
+        return PIGS_OK;
+    }
     NEED(h);
     std::vector<double> v((size_t)h->nvec);
     CK(cudaMemcpyAsync(v.data(), h->d_vec, sizeof(double) * h->nvec, cudaMemcpyDeviceToHost, h->st));
@@ -512,6 +726,7 @@ extern "C" int pigs_get_block(pigs_handle h, pigs_block_result* out, double* gr,
     return PIGS_OK;
 }
 extern "C" int pigs_get_block_chain(pigs_handle h, int chain, pigs_block_result* out, double* gr, double* Sk, double* nrho) {
+    MULTI_CHAIN(h, chain, pigs_get_block_chain(s_, lc_, out, gr, Sk, nrho));
     NEED(h); NEED_CHAIN(h, chain);
     const DevParams& P = h->P;
     std::vector<double> a((size_t)P.nacc), v((size_t)h->nvec);
@@ -525,7 +740,43 @@ extern "C" int pigs_get_block_chain(pigs_handle h, int chain, pigs_block_result*
     unpack(h, v.data(), out, gr, Sk, nrho);
     return PIGS_OK;
 }
+// per-chain results of the last block for chains [chain0, chain0 + n): ONE device->host copy of the accumulators
+// and one of the counters (the statistics layer needs every chain's block; a getter per chain costs n round trips)
+extern "C" int pigs_get_block_chains(pigs_handle h, int chain0, int n, pigs_block_result* out, double* gr, double* Sk, double* nrho) {
+    if (h && !h->sub.empty()) {
+        if (n < 0 || chain0 < 0 || chain0 + n > h->hp.n_chains) return fail(PIGS_E_ARG, "chain range out of bounds");
+        const size_t ngr = h->P.Nbin, nsk = (size_t)h->P.dim * h->P.Nk, nnr = (size_t)h->P.Nbin * (h->P.Npw + 1);
+        for (size_t k = 0; k < h->sub.size(); ++k) {
+            const int lo = std::max(chain0, h->first[k]), hi = std::min(chain0 + n, h->first[k + 1]);
+            if (lo >= hi) continue;
+            const size_t o = (size_t)(lo - chain0);
+            int rc = pigs_get_block_chains(h->sub[k], lo - h->first[k], hi - lo, out ? out + o : nullptr, gr ? gr + o * ngr : nullptr,
+                                           Sk ? Sk + o * nsk : nullptr, nrho ? nrho + o * nnr : nullptr);
+            if (rc) return rc;
+        }
+        return PIGS_OK;
+    }
+    NEED(h);
+    if (n < 0 || chain0 < 0 || chain0 + n > h->hp.n_chains) return fail(PIGS_E_ARG, "chain range out of bounds");
+    if (n == 0) return PIGS_OK;
+    const DevParams& P = h->P;
+    std::vector<double> a((size_t)n * P.nacc), v((size_t)h->nvec);
+    std::vector<long long> c((size_t)n * NCNT);
+    CK(cudaMemcpyAsync(a.data(), h->d_acc + (size_t)chain0 * P.nacc, sizeof(double) * a.size(), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(c.data(), h->d_cnt + (size_t)chain0 * NCNT, sizeof(long long) * c.size(), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    const size_t ngr = P.Nbin, nsk = (size_t)P.dim * P.Nk, nnr = (size_t)P.Nbin * (P.Npw + 1);
+    for (int k = 0; k < n; ++k) {
+        const double* ak = a.data() + (size_t)k * P.nacc;
+        for (int i = 0; i < NE; ++i) v[i] = ak[i];
+        for (int i = 0; i < NCNT; ++i) v[NE + i] = (double)c[(size_t)k * NCNT + i];
+        for (int i = NE; i < P.nacc; ++i) v[NCNT + i] = ak[i];
+        unpack(h, v.data(), out ? out + k : nullptr, gr ? gr + k * ngr : nullptr, Sk ? Sk + k * nsk : nullptr, nrho ? nrho + k * nnr : nullptr);
+    }
+    return PIGS_OK;
+}
 extern "C" int pigs_block_vector(pigs_handle h, double** dev_ptr, int* n) {
+    if (h && !h->sub.empty()) return fail(PIGS_E_ARG, "pigs_block_vector: a multi-GPU handle reduces by itself (pigs_get_block)");
     NEED(h);
     if (dev_ptr) *dev_ptr = h->d_vec;
     if (n) *n = h->nvec;
@@ -533,12 +784,20 @@ extern "C" int pigs_block_vector(pigs_handle h, double** dev_ptr, int* n) {
 }
 extern "C" int pigs_unpack_block_vector(pigs_handle h, const double* vec, pigs_block_result* out, double* gr, double* Sk, double* nrho) {
     if (!h || !vec) return fail(PIGS_E_ARG, "null argument");
+    if (!h->sub.empty()) h = h->sub[0];
     unpack(h, vec, out, gr, Sk, nrho);
     return PIGS_OK;
 }
 
 // ---- unit API ----------------------------------------------------------------------------------
 extern "C" int pigs_move(pigs_handle h, int move, int ip, int half, int32_t* accepted, int32_t* aux) {
+    if (h && !h->sub.empty()) {
+        for (size_t k = 0; k < h->sub.size(); ++k) {
+            int rc = pigs_move(h->sub[k], move, ip, half, accepted ? accepted + h->first[k] : nullptr, aux ? aux + h->first[k] : nullptr);
+            if (rc) return rc;
+        }
+        return PIGS_OK;
+    }
     NEED(h);
     if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
     if (move < 0 || move > 13) return fail(PIGS_E_ARG, "unknown move");
@@ -569,6 +828,7 @@ struct DevBuf {
 
 extern "C" int pigs_update_action(pigs_handle h, int n, const double* R, const int32_t* ip, const int32_t* ib,
                                   const double* xnew, const double* xold, double* DeltaS) {
+    MULTI(h, pigs_update_action(h->sub[0], n, R, ip, ib, xnew, xold, DeltaS));
     NEED(h);
     if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
     if (n < 0 || !R || !ip || !ib || !xnew || !xold || !DeltaS) return fail(PIGS_E_ARG, "bad argument");
@@ -588,8 +848,12 @@ extern "C" int pigs_update_action(pigs_handle h, int n, const double* R, const i
     CK(cudaMemcpyAsync(dxn.p, xnew, (size_t)n * P.dim * sizeof(double), cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(dxo.p, xold, (size_t)n * P.dim * sizeof(double), cudaMemcpyHostToDevice, h->st));
     { std::lock_guard<std::mutex> lk(g_launch_mutex);
-    CK(launch_update_action(P.trap, P, n, (const double*)dR.p, (const int*)dip.p, (const int*)dib.p, (const double*)dxn.p,
-                            (const double*)dxo.p, (double*)dS.p, h->st)); }
+    int rc = guard_enter(h);
+    if (rc) return rc;
+    CK(launch_update_action(P.trap, h->var == 2, P, n, (const double*)dR.p, (const int*)dip.p, (const int*)dib.p, (const double*)dxn.p,
+                            (const double*)dxo.p, (double*)dS.p, h->st));
+    rc = guard_leave(h);
+    if (rc) return rc; }
     h->launches += 1;
     CK(cudaMemcpyAsync(DeltaS, dS.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -604,13 +868,18 @@ static int unit_call(pigs_ctx* h, int op, int n, const std::vector<double>& in, 
     if (out_init) CK(cudaMemcpyAsync(dout.p, out_init, (size_t)n * out_per * sizeof(double), cudaMemcpyHostToDevice, h->st));
     UnitArgs A; A.op = op; A.n = n; A.in = (const double*)din.p; A.out = (double*)dout.p;
     { std::lock_guard<std::mutex> lk(g_launch_mutex);
-    CK(launch_unit(h->P.trap, h->P, A, h->st)); }
+    int rc = guard_enter(h);
+    if (rc) return rc;
+    CK(launch_unit(h->P.trap, h->P, A, h->st));
+    rc = guard_leave(h);
+    if (rc) return rc; }
     h->launches += 1;
     CK(cudaMemcpyAsync(out, dout.p, (size_t)n * out_per * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     return PIGS_OK;
 }
 extern "C" int pigs_local_energy(pigs_handle h, int n, const double* R, double* E, double* Kin, double* Pot) {
+    MULTI(h, pigs_local_energy(h->sub[0], n, R, E, Kin, Pot));
     NEED(h);
     if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
     if (n < 0 || !R) return fail(PIGS_E_ARG, "bad argument");
@@ -623,6 +892,7 @@ extern "C" int pigs_local_energy(pigs_handle h, int n, const double* R, double* 
     return PIGS_OK;
 }
 extern "C" int pigs_therm_energy(pigs_handle h, int n, const double* Path, double* E, double* Ec, double* Ep) {
+    MULTI(h, pigs_therm_energy(h->sub[0], n, Path, E, Ec, Ep));
     NEED(h);
     if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
     if (n < 0 || !Path) return fail(PIGS_E_ARG, "bad argument");
@@ -635,6 +905,7 @@ extern "C" int pigs_therm_energy(pigs_handle h, int n, const double* Path, doubl
     return PIGS_OK;
 }
 extern "C" int pigs_pair_correlation(pigs_handle h, int n, const double* R, double* gr) {
+    MULTI(h, pigs_pair_correlation(h->sub[0], n, R, gr));
     NEED(h);
     if (h->P.trap) return fail(PIGS_E_ARG, "PairCorrelation is not defined in trap mode (vpi.f90:466)");
     if (n < 0 || !R || !gr) return fail(PIGS_E_ARG, "bad argument");
@@ -644,6 +915,7 @@ extern "C" int pigs_pair_correlation(pigs_handle h, int n, const double* R, doub
     return unit_call(h, U_PAIR_CORR, n, soa, h->P.Nbin, gr, gr);
 }
 extern "C" int pigs_structure_factor(pigs_handle h, int n, const double* R, double* Sk) {
+    MULTI(h, pigs_structure_factor(h->sub[0], n, R, Sk));
     NEED(h);
     if (h->P.trap) return fail(PIGS_E_ARG, "StructureFactor is not defined in trap mode (vpi.f90:466)");
     if (n < 0 || !R || !Sk) return fail(PIGS_E_ARG, "bad argument");
@@ -653,6 +925,7 @@ extern "C" int pigs_structure_factor(pigs_handle h, int n, const double* R, doub
     return unit_call(h, U_SOFK, n, soa, (size_t)h->P.Nk * h->P.dim, Sk, Sk);
 }
 extern "C" int pigs_obdm(pigs_handle h, int n, const double* xend, double* nrho) {
+    MULTI(h, pigs_obdm(h->sub[0], n, xend, nrho));
     NEED(h);
     if (h->P.trap) return fail(PIGS_E_ARG, "OBDM is not defined in trap mode (vpi.f90:400)");
     if (n < 0 || !xend || !nrho) return fail(PIGS_E_ARG, "bad argument");

@@ -53,6 +53,7 @@ struct DevParams {
     int dim, Np, Nb, S, NpS, Nmax, Nbin, Nk, Npw;
     int trap, sampling, Lstag, Nlev, Nstag, Nobdm, swapping, CMFreq;
     int n_chains;
+    int chain_offset;         // global index of chain 0 (chains of one run sharded over several handles)
     double L[3], Lh[3], invL[3], qbin[3], a_ho[3];
     double rcut2, dr, inv_dr, rbin, dt, delta_cm, CWorm, density, pi, logCd;
     // GreenFunction (global_mod.f90:19-72) as weights by slice class [even, odd, end]: action (opt 0) and its
@@ -78,7 +79,7 @@ struct DevParams {
     int* cyc;                 // [chain][Np]  Particles_in_perm_cycle
     int* hist;                // [chain][Np]  Perm_histogram
     unsigned* mt;             // [chain][624]
-    unsigned long long* pctr; // [chain] Philox counter
+    unsigned long long* pctr; // [chain][PCS] Philox counters
     double* acc;              // [chain][nacc]
     long long* cnt;           // [chain][NCNT]
     size_t chain_stride;      // doubles per chain in path
@@ -95,6 +96,7 @@ struct SweepArgs {
     int chain_only;      // >=0: only that chain (OP_UNIFORM/OP_GAUSS/OP_SEED)
     int seed;            // OP_SEED
     int groups_per_cta, threads_per_chain, tshift;   // T = 1 << tshift
+    int team;            // 1: T = 128 and the four warps of a group sweep disjoint slice windows concurrently (Philox only)
     int prefetch;        // 0 off, 1 L1 line prefetch at move start, 2 L2 bulk per phase, 3 L2 bulk rolling (default)
     int pfdist;          // rolling distance in beads (PIGS_PFDIST)
     int* accepted;       // OP_MOVE [n_chains]
@@ -107,24 +109,6 @@ struct SweepArgs {
 static __constant__ DevParams cP;
 static __constant__ SweepArgs cA;
 
-// ------------------------------------------------------------------ group
-struct Grp {
-    int tid, lane, warp, nwarps, size;
-};
-__device__ __forceinline__ Grp grp() {
-    Grp g;
-    g.size = cA.threads_per_chain;
-    g.tid = threadIdx.x & (g.size - 1);
-    g.lane = threadIdx.x & 31;
-    g.warp = g.tid >> 5;
-    g.nwarps = g.size >> 5;
-    return g;
-}
-__device__ __forceinline__ void gsync() {
-    if (cA.threads_per_chain == 32) __syncwarp();
-    else asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x >> cA.tshift)), "r"(cA.threads_per_chain) : "memory");
-}
-
 // per-group state in shared memory: header + arrays
 // Move descriptor + RNG state parked in shared memory across the partner loop
 // (run_move, pigs_sweep.cuh); ctr ping-pongs by phase parity.
@@ -132,7 +116,10 @@ struct RngS {
     unsigned long long ctr;
     unsigned w0, w1, w2;
     int nleft;
+    unsigned tag;        // Philox stream selector: 0 the chain's stream, 1 + w the stream of window worker w
+    unsigned pad;
 };
+constexpr int PCS = 8;   // Philox counters kept per chain: [0] chain stream, [1 + w] window workers
 struct MovePark {
     RngS ctr[2];
     double Sbase, DeltaK;
@@ -152,10 +139,38 @@ struct GS {
     long long cnt[NCNT];
     int ibc[8];
     // chain state (written by thread 0, read by all after a group sync)
-    int mti, isopen, iworm0, iperm, new_pc, end_pc, ik0, swap_acc, idiag_aux, chain, pad0, pad1;
+    int mti, isopen, iworm0, iperm, new_pc, end_pc, ik0, swap_acc, idiag_aux, chain;
+    // Geometry of the thread group that currently works on this block (set by thread 0 of the owner, read after a
+    // sync): normally the chain group of T threads; in team mode one warp (a window worker) during the sweeps.
+    int gsize, gshift, gbar;
+    int pad0, pad1, pad2;
     MovePark pk;
     // followed by: seg_old[3S] seg_new[3S] part[np*8] pp[Np]
 };
+// ------------------------------------------------------------------ group
+struct Grp {
+    int tid, lane, warp, nwarps, size;
+};
+__device__ __forceinline__ Grp grp(const GS* gs) {
+    Grp g;
+    g.size = gs->gsize;
+    g.tid = threadIdx.x & (g.size - 1);
+    g.lane = threadIdx.x & 31;
+    g.warp = g.tid >> 5;
+    g.nwarps = g.size >> 5;
+    return g;
+}
+__device__ __forceinline__ void gsync(const GS* gs) {
+    const int n = gs->gsize;
+    if (n == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(gs->gbar), "r"(n) : "memory");
+}
+// all T threads of the chain group, whatever the current working geometry (team mode: the four window workers)
+__device__ __forceinline__ void tsync() {
+    if (cA.threads_per_chain == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x >> cA.tshift)), "r"(cA.threads_per_chain) : "memory");
+}
+__device__ __forceinline__ bool gfirst(const GS* gs) { return (threadIdx.x & (gs->gsize - 1)) == 0; }
 __host__ __device__ inline int part_slots(int nwarps) { return nwarps < 4 ? 4 : nwarps; }
 __host__ __device__ inline size_t grp_smem_bytes(int S, int Np, int nwarps) {
     return sizeof(GS) + sizeof(double) * ((size_t)6 * S + (size_t)part_slots(nwarps) * 8 + (size_t)Np);
@@ -405,8 +420,8 @@ static __device__ __noinline__ double mt_rangauss(GS* gs) {                // ra
 }
 
 // Philox4x32-10 (Salmon et al., SC'11); counter = (ctr_lo, ctr_hi, chain, tag), key = seed
-static __device__ __noinline__ uint4 philox_at(unsigned long long c, unsigned chain) {
-    uint4 x = make_uint4((unsigned)c, (unsigned)(c >> 32), chain, 0x50494753u);
+static __device__ __noinline__ uint4 philox_at(unsigned long long c, unsigned chain, unsigned tag) {
+    uint4 x = make_uint4((unsigned)c, (unsigned)(c >> 32), chain, 0x50494753u + tag);
     unsigned k0 = (unsigned)cP.seed, k1 = (unsigned)(cP.seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -430,14 +445,14 @@ __device__ __forceinline__ double u01_from(unsigned lo, unsigned hi) {        //
 template <bool MT>
 __device__ __forceinline__ double rng_uniform(GS* gs, RngS& st) {
     if (MT) {
-        gsync();
-        if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) gs->bc[0] = mt_grnd(gs);
-        gsync();
+        gsync(gs);
+        if (gfirst(gs)) gs->bc[0] = mt_grnd(gs);
+        gsync(gs);
         return gs->bc[0];
     } else {
         unsigned x;
         if (st.nleft == 0) {
-            uint4 r = philox_at(st.ctr, (unsigned)gs->chain);
+            uint4 r = philox_at(st.ctr, (unsigned)gs->chain, st.tag);
             st.ctr += 1;
             x = r.x; st.w0 = r.y; st.w1 = r.z; st.w2 = r.w; st.nleft = 3;
         } else {
@@ -451,7 +466,7 @@ __device__ __forceinline__ double rng_uniform(GS* gs, RngS& st) {
 // Ends with a group sync.
 template <bool MT>
 __device__ __forceinline__ void rng_gauss_fill(GS* gs, RngS* pst, int dim, int b0, int bstride, int nb) {
-    const Grp G = grp();
+    const Grp G = grp(gs);
     const int n = nb * dim;
     double* dst = seg_new(gs);
     if (MT) {
@@ -465,14 +480,14 @@ __device__ __forceinline__ void rng_gauss_fill(GS* gs, RngS* pst, int dim, int b
         unsigned long long ctr = pst->ctr;
         for (int i = G.tid; i < n; i += G.size) {
             int j = dim == 3 ? (i * 43691) >> 17 : (dim == 2 ? i >> 1 : i), k = i - j * dim;
-            uint4 r = philox_at(ctr + (unsigned long long)i, (unsigned)gs->chain);
+            uint4 r = philox_at(ctr + (unsigned long long)i, (unsigned)gs->chain, pst->tag);
             double u1 = 1.0 - u01_from(r.x, r.y);       // (0,1]
             double u2 = u01_from(r.z, r.w);
             dst[k * cP.S + b0 + j * bstride] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
         }
         pst->ctr = ctr + (unsigned long long)n;
     }
-    gsync();
+    gsync(gs);
 }
 
 // ------------------------------------------------------------------ the pair sums of one bead-update

@@ -20,7 +20,11 @@ __global__ void __launch_bounds__(PIGS_MAXT, 1) PIGS_KNAME() { sweep_body<(PIGS_
 cudaError_t PIGS_LNAME(int what, const DevParams* P, const SweepArgs* A, int grid, int block, size_t smem,
                        cudaStream_t st, int* out) {
     if (what == 0) {
-        cudaError_t e = cudaMemcpyToSymbolAsync(cP, P, sizeof(DevParams), 0, cudaMemcpyHostToDevice, st);
+        // the attribute belongs to the function (per device), not to a handle: two handles with different
+        // shared-memory footprints share this kernel, so it is set for every launch
+        cudaError_t e = cudaFuncSetAttribute(PIGS_KNAME, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyToSymbolAsync(cP, P, sizeof(DevParams), 0, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) return e;
         e = cudaMemcpyToSymbolAsync(cA, A, sizeof(SweepArgs), 0, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) return e;

@@ -22,10 +22,10 @@ struct UnitArgs {
     double* out;         // [n][3] energies / histograms [n][...]
 };
 cudaError_t launch_unit(bool trap, const DevParams& P, const UnitArgs& A, cudaStream_t st);
-cudaError_t launch_update_action(bool trap, const DevParams& P, int n, const double* Rsoa, const int* ip, const int* ib,
+cudaError_t launch_update_action(bool trap, bool smem_tables, const DevParams& P, int n, const double* Rsoa, const int* ip, const int* ib,
                                  const double* xnew, const double* xold, double* dS, cudaStream_t st);
 // layout transposes between the ABI's Path(dim,Np,0:2Nb) and the internal SoA
-cudaError_t launch_aos_to_soa(const DevParams& P, const double* aos, double* soa, int nchain, cudaStream_t st);
+cudaError_t launch_aos_to_soa(const DevParams& P, const double* aos, double* soa, int nchain, cudaStream_t st, int* flag);
 cudaError_t launch_soa_to_aos(const DevParams& P, const double* soa, double* aos, int nchain, cudaStream_t st);
 // chain-summed block vector [NE | NCNT | gr | Sk | nrho]
 cudaError_t launch_reduce_block(const DevParams& P, double* vec, cudaStream_t st);

@@ -48,7 +48,7 @@ template <int VAR> __device__ __forceinline__ double wrap_lt(int k, double d) { 
     return PIGS_TRAP ? d : mimg_lt_first(d, cP.L[k], cP.Lh[k]);
 }
 __device__ __forceinline__ void bump(GS* gs, int c) {
-    if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) gs->cnt[c] += 1;
+    if (gfirst(gs)) gs->cnt[c] += 1;
 }
 
 // ---------------------------------------------------------------- small-integer helpers (no IDIV in hot code)
@@ -65,7 +65,7 @@ __device__ __forceinline__ int div_dim(int i) {          // i / cP.dim for dim i
 template <int VAR>
 static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, int bstride, int nb, double wfirst,
                                                       double wlast, bool roll) {
-    const Grp G = grp();
+    const Grp G = grp(gs);
     if (G.tid == 0) {
         // bead-update counters by slice class, in closed form (beads b0, b0+bstride, ...)
         const int last = b0 + (nb - 1) * bstride;
@@ -152,10 +152,10 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
     double S = 0.0;
     if (split == 1) {
         if (G.lane == 0) part[G.warp] = Sw;
-        gsync();
+        gsync(gs);
         for (int w = 0; w < nw; ++w) S += part[w];
     } else {
-        gsync();
+        gsync(gs);
         for (int m = 0; m < nb; ++m) {
             double v[8];
 #pragma unroll
@@ -168,7 +168,7 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
             S += w * assemble_dS(b0 + m * bstride, v);
         }
     }
-    gsync();
+    gsync(gs);
     return S;
 }
 PIGS_T __device__ __forceinline__ double uniform(GS* gs, ull& ctr) { return rng_uniform<MT>(gs, ctr); }
@@ -244,7 +244,7 @@ __device__ __forceinline__ PhaseGeom phase_geom(int flags, int ii, int ie, int m
 
 PIGS_T __device__ __forceinline__ void move_prologue(GS* gs, ull* pctr, int flags, int ip0, int ii, int ie, int m0, int m1,
                                                      double Sbase) {
-    const Grp G = grp();
+    const Grp G = grp(gs);
     ull ctr = *pctr;
     const int type = flags & MV_TYPE_MASK;
     const int half = (flags & MV_HALF_MASK) >> 2;
@@ -264,7 +264,7 @@ PIGS_T __device__ __forceinline__ void move_prologue(GS* gs, ull* pctr, int flag
     }
     if (half) {
         if (G.tid < dim) pth(gs, G.tid, ip0, cP.Nb) = gs->xend[(half - 1) * 3 + G.tid];
-        gsync();
+        gsync(gs);
     }
     // ---- load the segment (translate: shifted copy)
     {
@@ -281,14 +281,14 @@ PIGS_T __device__ __forceinline__ void move_prologue(GS* gs, ull* pctr, int flag
             if (type == MV_TRANSLATE && k < dim) v = bc_wrap<VAR>(k, v + ((k == 0) ? dx[0] : ((k == 1) ? dx[1] : dx[2])));
             sn(gs, k, ib) = v;
         }
-        gsync();
+        gsync(gs);
     }
     if (flags & (MV_GLUE_II_X1 | MV_GLUE_IE_X2)) {
         if (G.tid < dim) {
             if (flags & MV_GLUE_II_X1) sn(gs, G.tid, ii) = gs->xend[G.tid];
             else sn(gs, G.tid, ie) = gs->xend[3 + G.tid];
         }
-        gsync();
+        gsync(gs);
     }
     double DeltaK = 0.0;
     if (flags & MV_DK_OLD_ADD) DeltaK = link_DeltaK<VAR>(seg_old(gs), ii, ie, L);
@@ -303,7 +303,7 @@ PIGS_T __device__ __forceinline__ void move_prologue(GS* gs, ull* pctr, int flag
 
 // proposal of phase ph; returns the beads to evaluate and their end weights
 PIGS_T __device__ __forceinline__ void phase_pre(GS* gs, int ph, int& b0, int& bs, int& nb, double& wf, double& wl, bool& roll) {
-    const Grp G = grp();
+    const Grp G = grp(gs);
     const MovePark& pk = gs->pk;
     const int flags = pk.flags, ii = pk.ii, ie = pk.ie;
     const PhaseGeom g = phase_geom(flags, ii, ie, pk.m0, pk.m1, ph);
@@ -347,7 +347,7 @@ PIGS_T __device__ __forceinline__ void phase_pre(GS* gs, int ph, int& b0, int& b
                 }
             }
         }
-        gsync();
+        gsync(gs);
     } else if (type == MV_BISECT) {      // one bisection level (vpi_mod.f90:905-956)
         const double sigma = cP.sig_bis[g.Nl - g.lev + 1];        // delta_ib = 2^(Nl-lev+1)
         for (int i = G.tid; i < nb * dim; i += G.size) {
@@ -358,7 +358,7 @@ PIGS_T __device__ __forceinline__ void phase_pre(GS* gs, int ph, int& b0, int& b
             double xnext = xold - wrap_lt<VAR>(k, xold - sn(gs, k, inext));
             sn(gs, k, icurr) = bc_wrap<VAR>(k, 0.5 * (xprev + xnext) + sigma * gz);
         }
-        gsync();
+        gsync(gs);
     }
     wf = (type != MV_BISECT && (flags & MV_WFIRST_HALF)) ? 0.5 : 1.0;
     wl = (type != MV_BISECT && (flags & MV_WLAST_HALF)) ? 0.5 : 1.0;
@@ -387,7 +387,7 @@ PIGS_T __device__ __forceinline__ int phase_post(GS* gs, int ph, double S) {
     }
     pk.ctr[(ph + 1) & 1] = ctr;
     if (!accept) return 1;
-    gsync();
+    gsync(gs);
     const PhaseGeom g = phase_geom(flags, ii, ie, 0, 0, ph);
     return (ph + 1 == g.nphase) ? 2 : 0;
 }
@@ -419,7 +419,7 @@ PIGS_T __device__ __forceinline__ bool run_move_body(GS* gs, ull* pctr, int flag
         if (r) break;
     }
     asm volatile("" ::: "memory");
-    const Grp G = grp();
+    const Grp G = grp(gs);
     const MovePark& pk = gs->pk;
     const bool accept = (r == 2);
     if (accept) {
@@ -431,7 +431,7 @@ PIGS_T __device__ __forceinline__ bool run_move_body(GS* gs, ull* pctr, int flag
         }
     }
     const ull cfin = pk.ctr[(ph + 1) & 1];
-    gsync();
+    gsync(gs);
     *pctr = cfin;
     return accept;
 }
@@ -449,9 +449,9 @@ PIGS_T __device__ __forceinline__ void TranslateHalfChain(GS* gs, ull* pctr, int
     // cut bead at full weight (Q21)
     if (run_move<MT, VAR>(gs, pctr, MV_TRANSLATE | (half << 2), ip0, ibi, ibf, ibi, ibf, 0.0)) {
         bump(gs, C_ACC_CM_HALF);
-        const int t = threadIdx.x & (cA.threads_per_chain - 1);
+        const int t = threadIdx.x & (gs->gsize - 1);
         if (t < cP.dim) gs->xend[(half - 1) * 3 + t] = sn(gs, t, cP.Nb);
-        gsync();
+        gsync(gs);
     }
 }
 PIGS_T __device__ __forceinline__ void Staging(GS* gs, ull* pctr, int L, int ip0) {              // vpi_mod.f90:480-578
@@ -477,9 +477,9 @@ PIGS_T __device__ __forceinline__ void MoveHead(GS* gs, ull* pctr, int Lmax, int
     if (run_move<MT, VAR>(gs, pctr, fl, ip0, ii, ie, ii, ie - 1, 0.0)) {
         bump(gs, half ? C_ACC_HEAD_HALF : C_ACC_HEAD);
         if (half == 2) {       // the free end IS the cut bead
-            const int t = threadIdx.x & (cA.threads_per_chain - 1);
+            const int t = threadIdx.x & (gs->gsize - 1);
             if (t < cP.dim) gs->xend[3 + t] = sn(gs, t, cP.Nb);
-            gsync();
+            gsync(gs);
         }
     }
 }
@@ -493,9 +493,9 @@ PIGS_T __device__ __forceinline__ void MoveTail(GS* gs, ull* pctr, int Lmax, int
     if (run_move<MT, VAR>(gs, pctr, fl, ip0, ii, ie, ii + 1, ie, 0.0)) {
         bump(gs, half ? C_ACC_TAIL_HALF : C_ACC_TAIL);
         if (half == 1) {
-            const int t = threadIdx.x & (cA.threads_per_chain - 1);
+            const int t = threadIdx.x & (gs->gsize - 1);
             if (t < cP.dim) gs->xend[t] = sn(gs, t, cP.Nb);
-            gsync();
+            gsync(gs);
         }
     }
 }
@@ -520,7 +520,7 @@ PIGS_T __device__ __forceinline__ int draw_half(GS* gs, ull& ctr) { int h = (int
 
 // OpenChain (vpi_mod.f90:1821-2076) when open, CloseChain (:2080-2266) otherwise
 PIGS_T static __device__ __noinline__ void OpenClose(GS* gs, ull* pctr, int Lmax, int ip0, bool open) {
-    const int t = threadIdx.x & (cA.threads_per_chain - 1);
+    const int t = threadIdx.x & (gs->gsize - 1);
     ull ctr = *pctr;
     int Ls = draw_even_Ls<MT, VAR>(gs, ctr, Lmax), half = draw_half<MT, VAR>(gs, ctr);
     *pctr = ctr;
@@ -551,10 +551,10 @@ PIGS_T static __device__ __noinline__ void OpenClose(GS* gs, ull* pctr, int Lmax
             if (t == 0) gs->end_pc = 0;
         }
     }
-    gsync();
+    gsync(gs);
 }
 PIGS_T static __device__ __noinline__ void Swap(GS* gs, ull* pctr, int Lmax, int iw0) {          // vpi_mod.f90:2270-2487
-    const Grp G = grp();
+    const Grp G = grp(gs);
     ull ctr = *pctr;
     if (G.tid == 0) gs->swap_acc = 0;
     int Ls = draw_even_Ls<MT, VAR>(gs, ctr, Lmax), ii = cP.Nb - Ls, ie = cP.Nb;
@@ -573,14 +573,14 @@ PIGS_T static __device__ __noinline__ void Swap(GS* gs, ull* pctr, int Lmax, int
         }
         pp[ip] = exp(-0.5 * r2 * inv);
     }
-    gsync();
+    gsync(gs);
     if (G.tid == 0) {
         double Sw = 0.0;
         for (int ip = 0; ip < cP.Np; ++ip) Sw += pp[ip];
         gs->bc[4] = Sw;
     }
     double uran = uniform<MT, VAR>(gs, ctr);
-    gsync();
+    gsync(gs);
     const double Sw = gs->bc[4];
     if (G.tid == 0) {
         double sum = 0.0;
@@ -591,13 +591,13 @@ PIGS_T static __device__ __noinline__ void Swap(GS* gs, ull* pctr, int Lmax, int
         }
         gs->ibc[0] = ik;
     }
-    gsync();
+    gsync(gs);
     const int ik = gs->ibc[0];
     if (ik != iw0) {
         double xk[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 3; ++k) if (k < cP.dim) xk[k] = pth(gs, k, ik, ie);
-        gsync();                                   // everyone has read pp/ibc before pp is reused
+        gsync(gs);                                   // everyone has read pp/ibc before pp is reused
         for (int ip = G.tid; ip < cP.Np; ip += G.size) {
             double r2 = 0.0;
 #pragma unroll
@@ -608,14 +608,14 @@ PIGS_T static __device__ __noinline__ void Swap(GS* gs, ull* pctr, int Lmax, int
             }
             pp[ip] = exp(-0.5 * r2 * inv);
         }
-        gsync();
+        gsync(gs);
         if (G.tid == 0) {
             double Sk = 0.0;
             for (int ip = 0; ip < cP.Np; ++ip) Sk += pp[ip];
             gs->bc[5] = Sk;
         }
         double ug = uniform<MT, VAR>(gs, ctr);      // always consumed (vpi_mod.f90:2373)
-        gsync();
+        gsync(gs);
         const double Sk = gs->bc[5];
         if (ug <= Sw / Sk) {
             *pctr = ctr;
@@ -642,7 +642,7 @@ PIGS_T static __device__ __noinline__ void Swap(GS* gs, ull* pctr, int Lmax, int
             }
         }
     }
-    gsync();
+    gsync(gs);
     *pctr = ctr;
 }
 
@@ -650,8 +650,8 @@ PIGS_T static __device__ __noinline__ void Swap(GS* gs, ull* pctr, int Lmax, int
 // (arrays in global memory, scalars in the group's shared state).
 static __device__ __noinline__ void PermutationSampling(GS* gs, bool have_swap) {
     if (!cP.swapping) return;        // the reference indexes unallocated arrays here (Q22)
-    gsync();
-    if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) {
+    gsync(gs);
+    if (gfirst(gs)) {
         int* cyc = gs->cyc;
         int* hist = gs->hist;
         if (gs->new_pc) {
@@ -681,14 +681,14 @@ static __device__ __noinline__ void PermutationSampling(GS* gs, bool have_swap) 
             gs->end_pc = 0;
         }
     }
-    gsync();
+    gsync(gs);
 }
 
 // ---------------------------------------------------------------- estimators
 // sum of N doubles over the group, identical in every thread
 template <int N>
 __device__ __forceinline__ void group_sum(GS* gs, double (&v)[N]) {
-    const Grp G = grp();
+    const Grp G = grp(gs);
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
     if (G.nwarps == 1) return;
@@ -697,14 +697,14 @@ __device__ __forceinline__ void group_sum(GS* gs, double (&v)[N]) {
 #pragma unroll
         for (int i = 0; i < N; ++i) part[G.warp * 8 + i] = v[i];
     }
-    gsync();
+    gsync(gs);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         double s = 0.0;
         for (int w = 0; w < G.nwarps; ++w) s += part[w * 8 + i];
         v[i] = s;
     }
-    gsync();
+    gsync(gs);
 }
 
 // LocalEnergy (sample_mod.f90:154-319) of slice R (SoA).  Thread i owns particle i
@@ -712,7 +712,7 @@ __device__ __forceinline__ void group_sum(GS* gs, double (&v)[N]) {
 // out[0..2] = E, Kin, Pot (identical in every thread).
 template <int VAR>
 static __device__ __noinline__ void LocalEnergy(GS* gs, const double* Rx, double* out) {
-    const Grp G = grp();
+    const Grp G = grp(gs);
     const double* Ry = Rx + PY;
     const double* Rz = Rx + PZ;
     const double* tV = gs->tabV;
@@ -769,7 +769,7 @@ static __device__ __noinline__ void LocalEnergy(GS* gs, const double* Rx, double
 // weighted share directly; no per-slice reduction is needed.  out = E, Ec, Ep.
 template <int VAR>
 static __device__ __forceinline__ void ThermEnergy(GS* gs, double* out) {      // one call site per kernel: inlined (see run_move_body)
-    const Grp G = grp();
+    const Grp G = grp(gs);
     const int nitem = 2 * cP.Nb * cP.Np;
     const double dt = cP.dt;
     const double* tV = gs->tabV;
@@ -853,8 +853,8 @@ static __device__ __forceinline__ void ThermEnergy(GS* gs, double* out) {      /
 
 // PairCorrelation (sample_mod.f90:392-431): gr(bin) += 2 per pair.  Counts are
 // small integers, so atomic accumulation in any order is exact.
-static __device__ __noinline__ void PairCorrelation(const double* Rx, double* gr) {
-    const Grp G = grp();
+static __device__ __noinline__ void PairCorrelation(const GS* gs, const double* Rx, double* gr) {
+    const Grp G = grp(gs);
     const double* Ry = Rx + PY;
     const double* Rz = Rx + PZ;
     const int Np = cP.Np, half = Np / 2;
@@ -875,8 +875,8 @@ static __device__ __noinline__ void PairCorrelation(const double* Rx, double* gr
     }
 }
 // StructureFactor (sample_mod.f90:435-476): thread <-> (iq,k)
-static __device__ __noinline__ void StructureFactor(const double* Rx, double* Sk) {
-    const Grp G = grp();
+static __device__ __noinline__ void StructureFactor(const GS* gs, const double* Rx, double* Sk) {
+    const Grp G = grp(gs);
     for (int it = G.tid; it < cP.Nk * cP.dim; it += G.size) {
         int iq = it / cP.dim + 1, k = it - (iq - 1) * cP.dim;
         const double* X = Rx + 32 * k;
@@ -890,8 +890,8 @@ static __device__ __noinline__ void StructureFactor(const double* Rx, double* Sk
     }
 }
 // OBDM (sample_mod.f90:480-526)
-static __device__ __noinline__ void OBDM(const double* xend, double* nrho) {
-    if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) {
+static __device__ __noinline__ void OBDM(const GS* gs, const double* xend, double* nrho) {
+    if (gfirst(gs)) {
         double d[3] = {0, 0, 0}, r2 = 0.0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) if (k < cP.dim) {
@@ -956,8 +956,124 @@ PIGS_T __device__ __forceinline__ void diag_sweep(GS* gs, ull* pctr, int istep, 
         if (run_move_body<MT, VAR>(gs, pctr, flags, cip, ii, ie, m0, m1, 0.0)) bump(gs, cacc);
     }
 }
-PIGS_T __device__ __forceinline__ void mc_step(GS* gs, ull* pctr, int istep) {      // vpi.f90:297-475
-    const Grp G = grp();
+// The diagonal sweep of the PRODUCTION (Philox) mode: same moves, same counts per Monte-Carlo step as vpi.f90:412-439
+// (translate every particle, then Nstag passes in which every particle gets a head, a tail and a middle move), but
+// ordered by TIME-SLICE WINDOW instead of by particle: a pass draws its windows once (head length, tail length,
+// start of the middle segment -- the reference draws them per particle) and moves all Np particles on one window
+// before going to the next.  Every move is the reference's move and satisfies detailed balance on its own, and the
+// window is drawn independently of the configuration, so the stationary distribution is unchanged (checked
+// statistically against the oracle); MT19937 replay keeps the reference's order (diag_sweep).
+// Why: the Np moves of a window re-read the same <= 2^Nlev + 1 slices, which then come from L2 instead of HBM
+// (DRAM traffic per step falls to that of the translations), and -- team mode, cA.team -- the four warps of a
+// chain group can sweep four DISJOINT windows of the same chain at the same time (head | middle | middle | tail):
+// moves of different particles on disjoint slice sets commute exactly.  The only shared data of two concurrent
+// moves would be the anchor beads of one particle; the workers therefore walk the particles in orders rotated by
+// Np/4 and meet at a barrier every Np/8 moves, so no two of them ever hold the same particle.  (A team pass makes
+// two middle sweeps where the reference makes one; the middle windows are drawn inside the range the head and
+// tail windows leave free.)  Translations need the action of all slices: the team evaluates them together.
+struct WinPass {
+    int Lh, Lt;          // head / tail segment lengths of this pass
+    int iiM[2];          // start beads of the middle segments
+    int nM;              // how many of them are in use
+};
+template <int VAR>
+__device__ __forceinline__ WinPass draw_pass(GS* gs, ull& ctr, bool team) {
+    const bool bis = cP.sampling != 0;
+    const int twoNb = 2 * cP.Nb, Lm = bis ? (1 << cP.Nlev) : cP.Lstag;
+    const int nend = (bis ? cP.Nlev : cP.Lstag) - 1;
+    WinPass w;
+    const int dh = draw_int<false, VAR>(gs, ctr, nend), dt = draw_int<false, VAR>(gs, ctr, nend);
+    w.Lh = bis ? (1 << (dh + 2)) : dh + 2;
+    w.Lt = bis ? (1 << (dt + 2)) : dt + 2;
+    if (!team) {
+        w.iiM[0] = draw_int<false, VAR>(gs, ctr, twoNb - Lm + 1);
+        w.iiM[1] = 0;
+        w.nM = 1;
+    } else {
+        // interiors of the middle segments inside [Lh, 2Nb - Lt], Lm - 1 beads each, at a random offset
+        const int lo = w.Lh, span = twoNb - w.Lt - lo + 1;
+        int n = (span > 0) ? span / (Lm - 1) : 0;
+        if (n > 2) n = 2;
+        w.nM = n;
+        w.iiM[0] = w.iiM[1] = 0;
+        if (n > 0) {
+            const int off = draw_int<false, VAR>(gs, ctr, span - n * (Lm - 1) + 1);
+            w.iiM[0] = lo - 1 + off;
+            w.iiM[1] = w.iiM[0] + (Lm - 1);
+        }
+    }
+    return w;
+}
+template <int VAR>
+__device__ __forceinline__ void win_sweep(GS* gs0, GS* gsw, ull* pctr, ull* pwctr, int istep, int skip0) {
+    const int Np = cP.Np, twoNb = 2 * cP.Nb;
+    const bool team = cA.team != 0;
+    const int wk = team ? (int)((threadIdx.x & (cA.threads_per_chain - 1)) >> 5) : 0;
+    const bool bis = cP.sampling != 0;
+    const int Lm = bis ? (1 << cP.Nlev) : cP.Lstag;
+    const int ty = bis ? MV_BISECT : MV_BRIDGE;
+    const int nT = (istep % cP.CMFreq == 0) ? Np : 0;
+    const int nsub = team ? 1 : 3;                              // windows this thread walks per pass
+    const int chunk = team ? (Np >= 8 ? (Np >> 3) : 1) : Np;     // team barrier every `chunk` moves
+    const int rot = team ? wk * (Np >> 2) : 0;                   // rotated particle order of worker wk
+    const int total = nT + cP.Nstag * nsub * Np;
+    int sub = 0, k = 0, left = 0;       // position inside the pass; moves left until the next team barrier
+    WinPass wp;
+    wp.Lh = wp.Lt = 2; wp.iiM[0] = wp.iiM[1] = 0; wp.nM = 0;
+    for (int q = 0; q < total; ++q) {
+        GS* g;
+        ull* rs;
+        int flags, ip, ii, ie, m0, m1, cacc;
+        if (q < nT) {                   // TranslateChain, all threads of the chain group together
+            ip = q;
+            if (ip == skip0) continue;
+            g = gs0; rs = pctr;
+            bump(g, C_TRY_CM);
+            flags = MV_TRANSLATE; ii = 0; ie = twoNb; m0 = 0; m1 = twoNb; cacc = C_ACC_CM;
+        } else {
+            if (sub == 0 && k == 0) {   // a new pass: its windows, from the chain's stream (identical in every thread)
+                if (team) {
+                    tsync();
+                    if (q == nT) {      // first pass: gs0 becomes the block of window worker 0
+                        if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) { gs0->gsize = 32; gs0->gshift = 5; }
+                        tsync();
+                    }
+                }
+                ull c = *pctr;
+                wp = draw_pass<VAR>(gsw, c, team);
+                *pctr = c;
+                left = 0;
+            }
+            if (team && left == 0) { tsync(); left = chunk; }
+            left -= 1;
+            const int kk = k;
+            const int cs = team ? wk : sub;             // team: 0 head, 1|2 middle, 3 tail;  else 0 head, 1 tail, 2 middle
+            if (++k == Np) { k = 0; if (++sub == nsub) sub = 0; }
+            ip = kk + rot; if (ip >= Np) ip -= Np;
+            if (ip == skip0) continue;
+            g = gsw; rs = team ? pwctr : pctr;
+            const bool head = cs == 0, tail = team ? cs == 3 : cs == 1;
+            if (head) {                 // MoveHead / MoveHeadBisection
+                bump(g, C_TRY_STAG);
+                flags = ty | MV_FREE_NEXT; ii = 0; ie = wp.Lh; m0 = 0; m1 = ie - 1; cacc = C_ACC_HEAD;
+            } else if (tail) {          // MoveTail / MoveTailBisection
+                flags = ty | MV_FREE_PREV; ie = twoNb; ii = ie - wp.Lt; m0 = ii + 1; m1 = ie; cacc = C_ACC_TAIL;
+            } else {                    // Staging / Bisection
+                const int j = team ? cs - 1 : 0;
+                if (j >= wp.nM) continue;
+                flags = ty; ii = wp.iiM[j]; ie = ii + Lm; m0 = ii + 1; m1 = ie - 1; cacc = C_ACC_BD;
+            }
+        }
+        if (run_move_body<false, VAR>(g, rs, flags, ip, ii, ie, m0, m1, 0.0)) bump(g, cacc);
+    }
+    if (team) {                         // back to the chain group's own geometry
+        tsync();
+        if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) { gs0->gsize = cA.threads_per_chain; gs0->gshift = cA.tshift; }
+        tsync();
+    }
+}
+PIGS_T __device__ __forceinline__ void mc_step(GS* gs, GS* gsw, ull* pctr, ull* pwctr, int istep) {      // vpi.f90:297-475
+    const Grp G = grp(gs);
     ull ctr = *pctr;
     int iupdate = (int)(uniform<MT, VAR>(gs, ctr) * 2.0);
     if (gs->isopen) {
@@ -971,9 +1087,9 @@ PIGS_T __device__ __forceinline__ void mc_step(GS* gs, ull* pctr, int istep) {  
     } else {
         if (iupdate == 1) {
             int iw = draw_int<MT, VAR>(gs, ctr, cP.Np);
-            gsync();
+            gsync(gs);
             if (G.tid == 0) gs->iworm0 = iw;
-            gsync();
+            gsync(gs);
             *pctr = ctr;
             OpenClose<MT, VAR>(gs, pctr, cP.Lstag, iw, true);
             ctr = *pctr;
@@ -982,13 +1098,15 @@ PIGS_T __device__ __forceinline__ void mc_step(GS* gs, ull* pctr, int istep) {  
         }
     }
     *pctr = ctr;
-    gsync();
+    gsync(gs);
     const bool is_open = gs->isopen;
     if (!is_open) {
         if (G.tid == 0) gs->idiag_aux += 1;
         bump(gs, C_IDIAG);
     }
-    diag_sweep<MT, VAR>(gs, pctr, istep, is_open ? gs->iworm0 : -1);       // the one inlined instance of the engine
+    // the one inlined instance of the engine: reference order under MT19937 replay, window order in production
+    if (MT) diag_sweep<MT, VAR>(gs, pctr, istep, is_open ? gs->iworm0 : -1);
+    else win_sweep<VAR>(gs, gsw, pctr, pwctr, istep, is_open ? gs->iworm0 : -1);
     if (is_open) {
         const int iw = gs->iworm0;
         for (int iobdm = 0; iobdm < cP.Nobdm; ++iobdm) {
@@ -1007,7 +1125,7 @@ PIGS_T __device__ __forceinline__ void mc_step(GS* gs, ull* pctr, int istep) {  
                 Swap<MT, VAR>(gs, pctr, cP.Lstag, iw);
                 PermutationSampling(gs, true);
             }
-            if (!PIGS_TRAP) { OBDM(gs->xend, gs->acc + cP.off_nr); gsync(); }
+            if (!PIGS_TRAP) { OBDM(gs, gs->xend, gs->acc + cP.off_nr); gsync(gs); }
         }
     } else {
         double e1[3], e2[3], et[3];
@@ -1024,8 +1142,8 @@ PIGS_T __device__ __forceinline__ void mc_step(GS* gs, ull* pctr, int istep) {  
         }
         bump(gs, C_NGR);
         if (!PIGS_TRAP) {
-            PairCorrelation(slice(gs, cP.Nb), gs->acc + cP.off_gr);
-            StructureFactor(slice(gs, cP.Nb), gs->acc + cP.off_sk);
+            PairCorrelation(gs, slice(gs, cP.Nb), gs->acc + cP.off_gr);
+            StructureFactor(gs, slice(gs, cP.Nb), gs->acc + cP.off_sk);
         }
     }
 }
@@ -1044,9 +1162,9 @@ PIGS_T __device__ __forceinline__ void do_move(GS* gs, ull* pctr, int move, int 
     case 9: MoveHead<MT, VAR>(gs, pctr, cP.Lstag, ip0, half); break;
     case 10: MoveTail<MT, VAR>(gs, pctr, cP.Lstag, ip0, half); break;
     case 11:
-        gsync();
-        if ((threadIdx.x & (cA.threads_per_chain - 1)) == 0) gs->iworm0 = ip0;
-        gsync();
+        gsync(gs);
+        if (gfirst(gs)) gs->iworm0 = ip0;
+        gsync(gs);
         OpenClose<MT, VAR>(gs, pctr, cP.Lstag, ip0, true);
         break;
     case 12: OpenClose<MT, VAR>(gs, pctr, cP.Lstag, ip0, false); break;
@@ -1080,41 +1198,54 @@ PIGS_T __device__ __forceinline__ void sweep_body() {
     const int g = threadIdx.x >> cA.tshift;
     const int tid = threadIdx.x & (T - 1);
     if (g >= Gn) return;
+    // team mode: four blocks per chain group, one per window worker (= warp); block 0 is also the group's own
+    const bool team = cA.team != 0;
+    const int wk = team ? (tid >> 5) : 0;
     const size_t gbytes = grp_smem_bytes(cP.S, cP.Np, T >> 5);
-    GS* gs = reinterpret_cast<GS*>(reinterpret_cast<char*>(sp) + (size_t)g * gbytes);
+    GS* gs = reinterpret_cast<GS*>(reinterpret_cast<char*>(sp) + (size_t)g * (team ? 4 : 1) * gbytes);
+    GS* gsw = reinterpret_cast<GS*>(reinterpret_cast<char*>(gs) + (size_t)wk * gbytes);
 
     for (int c = blockIdx.x * Gn + g; c < cP.n_chains; c += gridDim.x * Gn) {
         if (cA.chain_only >= 0 && c != cA.chain_only) continue;
         int* ist = cP.istate + (size_t)c * IS_N;
+        if ((tid & 31) == 0 && (tid == 0 || team)) {       // thread 0 fills the group's block, lane 0 of a worker warp its own
+            GS* b = gsw;
+            b->path = cP.path + (size_t)c * cP.chain_stride;
+            b->xend = cP.xend + (size_t)c * 6;
+            b->acc = cP.acc + (size_t)c * cP.nacc;
+            b->cyc = cP.cyc + (size_t)c * cP.Np;
+            b->hist = cP.hist + (size_t)c * cP.Np;
+            b->mt = cP.mt + (size_t)c * 624;
+            b->tabV = tV; b->tabW = tW;
+            b->chain = c + cP.chain_offset;
+            b->gsize = tid == 0 ? T : 32; b->gshift = tid == 0 ? cA.tshift : 5; b->gbar = g;
+        }
         if (tid == 0) {
-            gs->path = cP.path + (size_t)c * cP.chain_stride;
-            gs->xend = cP.xend + (size_t)c * 6;
-            gs->acc = cP.acc + (size_t)c * cP.nacc;
-            gs->cyc = cP.cyc + (size_t)c * cP.Np;
-            gs->hist = cP.hist + (size_t)c * cP.Np;
-            gs->mt = cP.mt + (size_t)c * 624;
-            gs->tabV = tV; gs->tabW = tW;
             gs->mti = ist[IS_MTI]; gs->isopen = ist[IS_OPEN]; gs->iworm0 = ist[IS_IWORM] - 1; gs->iperm = ist[IS_IPERM];
             gs->new_pc = ist[IS_NEWPC]; gs->end_pc = ist[IS_ENDPC]; gs->ik0 = ist[IS_IK] - 1; gs->swap_acc = 0;
-            gs->idiag_aux = ist[IS_IDIAG_AUX]; gs->chain = c;
+            gs->idiag_aux = ist[IS_IDIAG_AUX];
         }
         if (tid < NE) gs->eacc[tid] = 0.0;
-        if (tid < NCNT) gs->cnt[tid] = 0;
-        ull ctr;
-        ctr.ctr = cP.pctr[c]; ctr.w0 = ctr.w1 = ctr.w2 = 0u; ctr.nleft = 0;
-        gsync();
+        if ((tid & 31) < NCNT && (tid < 32 || team)) gsw->cnt[tid & 31] = 0;
+        ull ctr, wctr;
+        ctr.ctr = cP.pctr[(size_t)c * PCS]; ctr.w0 = ctr.w1 = ctr.w2 = 0u; ctr.nleft = 0; ctr.tag = 0u; ctr.pad = 0u;
+        wctr = ctr;
+        if (team) { wctr.ctr = cP.pctr[(size_t)c * PCS + 1 + wk]; wctr.tag = 1u + (unsigned)wk; }
+        tsync();
 
         if (cA.op == OP_BLOCK) {
-            for (int istep = 1; istep <= cA.nstep; ++istep) { mc_step<MT, VAR>(gs, &ctr, istep); gsync(); }
+            for (int istep = 1; istep <= cA.nstep; ++istep) { mc_step<MT, VAR>(gs, gsw, &ctr, &wctr, istep); gsync(gs); }
             if (tid < NE) gs->acc[tid] = gs->eacc[tid];
             if (tid < NCNT) {
                 long long v = gs->cnt[tid];
+                if (team)
+                    for (int w = 1; w < 4; ++w) v += reinterpret_cast<GS*>(reinterpret_cast<char*>(gs) + (size_t)w * gbytes)->cnt[tid];
                 if (tid == C_NOPEN) v = gs->isopen;
                 cP.cnt[(size_t)c * NCNT + tid] = v;
             }
         } else if (cA.op == OP_MOVE) {
             do_move<MT, VAR>(gs, &ctr, cA.move, cA.ip0, cA.half);
-            gsync();
+            gsync(gs);
             if (tid == 0) {
                 long long nacc = 0;
                 for (int i = C_ACC_CM; i <= C_ACC_SWAP; ++i)
@@ -1133,19 +1264,20 @@ PIGS_T __device__ __forceinline__ void sweep_body() {
             for (int i = 0; i < cA.nstep; ++i) {
                 rng_gauss_fill<MT>(gs, &ctr, 1, 0, 1, 1);
                 if (tid == 0) cA.draws[i] = seg_new(gs)[0];
-                gsync();
+                gsync(gs);
             }
         } else if (cA.op == OP_SEED) {
-            if (tid == 0) mt_seed(gs->mt, gs->mti, (unsigned)(cA.seed + (cA.chain_only >= 0 ? 0 : c)));
+            if (tid == 0) mt_seed(gs->mt, gs->mti, (unsigned)(cA.seed + (cA.chain_only >= 0 ? 0 : c + cP.chain_offset)));
         }
-        gsync();
+        gsync(gs);
         if (tid == 0) {
             ist[IS_OPEN] = gs->isopen; ist[IS_IWORM] = gs->iworm0 + 1; ist[IS_IPERM] = gs->iperm;
             ist[IS_NEWPC] = gs->new_pc; ist[IS_ENDPC] = gs->end_pc; ist[IS_IK] = gs->ik0 + 1; ist[IS_IDIAG_AUX] = gs->idiag_aux;
             ist[IS_MTI] = gs->mti;
-            cP.pctr[c] = ctr.ctr;
+            cP.pctr[(size_t)c * PCS] = ctr.ctr;
         }
-        gsync();
+        if (team && (tid & 31) == 0) cP.pctr[(size_t)c * PCS + 1 + wk] = wctr.ctr;
+        gsync(gs);
     }
 }
 

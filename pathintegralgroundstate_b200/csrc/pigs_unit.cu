@@ -31,7 +31,7 @@ template <int VAR>
 __global__ void __launch_bounds__(128) k_unit(const __grid_constant__ UnitArgs A) {
     extern __shared__ __align__(16) double smem[];
     GS* gs = reinterpret_cast<GS*>(smem);
-    if (threadIdx.x == 0) { gs->tabV = cP.vtab; gs->tabW = cP.logwf; gs->chain = 0; }
+    if (threadIdx.x == 0) { gs->tabV = cP.vtab; gs->tabW = cP.logwf; gs->chain = 0; gs->gsize = 128; gs->gshift = 7; gs->gbar = 0; }
     __syncthreads();
     const size_t ss = (size_t)3 * cP.NpS;
     for (int n = blockIdx.x; n < A.n; n += gridDim.x) {
@@ -46,11 +46,11 @@ __global__ void __launch_bounds__(128) k_unit(const __grid_constant__ UnitArgs A
             ThermEnergy<VAR>(gs, e);
             if (threadIdx.x == 0) { A.out[3 * n] = e[0]; A.out[3 * n + 1] = e[1]; A.out[3 * n + 2] = e[2]; }
         } else if (A.op == U_PAIR_CORR) {
-            PairCorrelation(A.in + n * ss, A.out + (size_t)n * cP.Nbin);
+            PairCorrelation(gs, A.in + n * ss, A.out + (size_t)n * cP.Nbin);
         } else if (A.op == U_SOFK) {
-            StructureFactor(A.in + n * ss, A.out + (size_t)n * cP.Nk * cP.dim);
+            StructureFactor(gs, A.in + n * ss, A.out + (size_t)n * cP.Nk * cP.dim);
         } else if (A.op == U_OBDM) {
-            OBDM(A.in + (size_t)n * 6, A.out + (size_t)n * cP.Nbin * (cP.Npw + 1));
+            OBDM(gs, A.in + (size_t)n * 6, A.out + (size_t)n * cP.Nbin * (cP.Npw + 1));
         }
         __syncthreads();
     }
@@ -81,10 +81,17 @@ cudaError_t launch_unit(bool trap, const DevParams& P, const UnitArgs& A, cudaSt
     return cudaGetLastError();
 }
 
-// UpdateAction (vpi_mod.f90:2491-2530): one warp per evaluation
-template <bool TRAP>
+// UpdateAction (vpi_mod.f90:2491-2530): one warp per evaluation.  SM: both tables staged in shared memory and read
+// through the zero tail exactly as the production sweep kernel (table_mode 2) does; else through L1/L2.
+template <bool TRAP, bool SM>
 __global__ void __launch_bounds__(128) k_update_action(int n, const double* Rsoa, const int* ip, const int* ib,
                                                       const double* xnew, const double* xold, double* dS) {
+    if (SM) {
+        extern __shared__ __align__(16) double pigs_smem_base[];
+        const int ntab = tab_len(cP.Nmax);
+        for (int i = threadIdx.x; i < ntab; i += blockDim.x) { pigs_smem_base[i] = cP.vtab[i]; pigs_smem_base[ntab + i] = cP.logwf[i]; }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (int e = w; e < n; e += nw) {
@@ -95,31 +102,42 @@ __global__ void __launch_bounds__(128) k_update_action(int n, const double* Rsoa
         Partner first;
         first.x = first.y = first.z = 0.0;
         if (lane < cP.Np) first = load_partner(Rx, lane);
-        double t = bead_eval<TRAP, false, false, false>(Rx, ip[e] - 1, ib[e], lane, 32, lane == 0, xo, xn, lane, nullptr, first);
+        double t = bead_eval<TRAP, SM, SM, false>(Rx, ip[e] - 1, ib[e], lane, 32, lane == 0, xo, xn, lane, nullptr, first);
         if (lane == 0) dS[e] = t;
     }
 }
-cudaError_t launch_update_action(bool trap, const DevParams& P, int n, const double* Rsoa, const int* ip, const int* ib,
+cudaError_t launch_update_action(bool trap, bool smem_tables, const DevParams& P, int n, const double* Rsoa, const int* ip, const int* ib,
                                  const double* xnew, const double* xold, double* dS, cudaStream_t st) {
     cudaError_t e = upload(P, 128, st);
     if (e != cudaSuccess) return e;
     int blocks = (n + 3) / 4;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    if (trap) k_update_action<true><<<blocks, 128, 0, st>>>(n, Rsoa, ip, ib, xnew, xold, dS);
-    else k_update_action<false><<<blocks, 128, 0, st>>>(n, Rsoa, ip, ib, xnew, xold, dS);
+    if (trap) k_update_action<true, false><<<blocks, 128, 0, st>>>(n, Rsoa, ip, ib, xnew, xold, dS);
+    else if (smem_tables) {
+        const size_t sm = (size_t)2 * tab_len(P.Nmax) * sizeof(double);
+        e = cudaFuncSetAttribute(k_update_action<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        if (blocks > 148) blocks = 148;
+        k_update_action<false, true><<<blocks, 128, sm, st>>>(n, Rsoa, ip, ib, xnew, xold, dS);
+    } else k_update_action<false, false><<<blocks, 128, 0, st>>>(n, Rsoa, ip, ib, xnew, xold, dS);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- layout transposes
 // aos: [chain][ib][ip][dim]  <->  blocked soa: [chain][ib][NpS/32][3][32]  (pidx, pigs_device.cuh)
-__global__ void k_aos_to_soa(const __grid_constant__ DevParams P, const double* aos, double* soa, long long nslice) {
+__global__ void k_aos_to_soa(const __grid_constant__ DevParams P, const double* aos, double* soa, long long nslice, int* flag) {
     const long long per = (long long)3 * P.NpS;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nslice * per; i += (long long)gridDim.x * blockDim.x) {
         long long s = i / per;
         int r = (int)(i - s * per), blk = r / PBLK, w = r - blk * PBLK, k = w >> 5, ip = blk * 32 + (w & 31);
         double v = 0.0;
-        if (k < P.dim && ip < P.Np) v = aos[(s * P.Np + ip) * P.dim + k];
+        if (k < P.dim && ip < P.Np) {
+            v = aos[(s * P.Np + ip) * P.dim + k];
+            // the action kernel takes ONE periodic image per component (as the reference does, pbc_mod.f90:29-52):
+            // coordinates must lie in the box [-L/2, L/2] (NaN is caught too)
+            if (!P.trap && flag && !(fabs(v) <= P.Lh[k] * (1.0 + 1e-12))) atomicOr(flag, 1);
+        }
         soa[i] = v;
     }
 }
@@ -131,9 +149,9 @@ __global__ void k_soa_to_aos(const __grid_constant__ DevParams P, const double* 
         aos[i] = soa[s * 3 * P.NpS + pidx(ip) + 32 * k];
     }
 }
-cudaError_t launch_aos_to_soa(const DevParams& P, const double* aos, double* soa, int nchain, cudaStream_t st) {
+cudaError_t launch_aos_to_soa(const DevParams& P, const double* aos, double* soa, int nchain, cudaStream_t st, int* flag) {
     long long nslice = (long long)nchain * P.S;
-    k_aos_to_soa<<<148 * 8, 256, 0, st>>>(P, aos, soa, nslice);
+    k_aos_to_soa<<<148 * 8, 256, 0, st>>>(P, aos, soa, nslice, flag);
     return cudaGetLastError();
 }
 cudaError_t launch_soa_to_aos(const DevParams& P, const double* soa, double* aos, int nchain, cudaStream_t st) {

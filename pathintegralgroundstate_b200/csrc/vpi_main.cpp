@@ -245,7 +245,7 @@ struct Config {
     double Rm = 0;
     std::vector<double> a_ho;
     // &cuda (not in the reference)
-    int n_chains = 1, threads_per_chain = 0, table_mode = -1;
+    int n_chains = 1, threads_per_chain = 0, table_mode = -1, schedule = -1;
     std::string rng, action;
     // crystal: config_ini.in line 2
     std::vector<double> Lbox_in;
@@ -291,7 +291,7 @@ Config read_vpi_in(const std::string& text) {
         for (auto& t : v->toks) c.a_ho.push_back(to_double(t));
     }
     I("cuda", "n_chains", c.n_chains, false); I("cuda", "threads_per_chain", c.threads_per_chain, false);
-    I("cuda", "table_mode", c.table_mode, false);
+    I("cuda", "table_mode", c.table_mode, false); I("cuda", "schedule", c.schedule, false);
     if (const Value* v = get("cuda", "rng")) c.rng = lower(v->toks[0]);
     if (const Value* v = get("cuda", "action")) c.action = lower(v->toks[0]);      // 'chin' | 'primitive' (global_mod.f90:48,67)
     if (!missing.empty()) {
@@ -537,6 +537,7 @@ int main(int argc, char** argv) {
     p.rng_mode = rng.rfind("mt", 0) == 0 ? PIGS_RNG_MT_REPLAY : PIGS_RNG_PHILOX;
     p.seed = (uint64_t)c.seed;
     p.device = device; p.threads_per_chain = c.threads_per_chain; p.table_mode = c.table_mode; p.action = c.action.rfind("prim", 0) == 0 ? 1 : 0;
+    p.schedule = c.schedule; p.chain_offset = 0;
     pigs_handle h = nullptr;
     CK(pigs_create(&p, &h));
     CK(pigs_set_tables(h, W.data(), V.data()));

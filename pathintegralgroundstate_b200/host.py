@@ -43,6 +43,7 @@ class PigsParams(C.Structure):
         ("Nstag", C.c_int32), ("Nobdm", C.c_int32), ("swapping", C.c_int32),
         ("n_chains", C.c_int32), ("rng_mode", C.c_int32), ("seed", C.c_uint64),
         ("device", C.c_int32), ("threads_per_chain", C.c_int32), ("table_mode", C.c_int32), ("action", C.c_int32),
+        ("schedule", C.c_int32), ("chain_offset", C.c_int32), ("gpus", C.c_int32),
     ]
 
 
@@ -100,11 +101,13 @@ def load_library() -> C.CDLL:
         "pigs_sync": (C.c_int, [H]),
         "pigs_get_block": (C.c_int, [H, C.POINTER(PigsBlockResult), dp, dp, dp]),
         "pigs_get_block_chain": (C.c_int, [H, C.c_int, C.POINTER(PigsBlockResult), dp, dp, dp]),
+        "pigs_get_block_chains": (C.c_int, [H, C.c_int, C.c_int, C.POINTER(PigsBlockResult), dp, dp, dp]),
         "pigs_block_vector": (C.c_int, [H, C.POINTER(C.c_void_p), ip]),
         "pigs_unpack_block_vector": (C.c_int, [H, dp, C.POINTER(PigsBlockResult), dp, dp, dp]),
         "pigs_last_block_ms": (C.c_int, [H, C.POINTER(C.c_float)]),
         "pigs_stream": (C.c_int, [H, C.POINTER(C.c_void_p)]),
         "pigs_launch_count": (C.c_int, [H, C.POINTER(C.c_int64)]),
+        "pigs_launch_plan": (C.c_int, [H, ip, ip, ip, ip, ip]),
         "pigs_move": (C.c_int, [H, C.c_int, C.c_int, C.c_int, i32p, i32p]),
         "pigs_update_action": (C.c_int, [H, C.c_int, dp, i32p, i32p, dp, dp, dp]),
         "pigs_local_energy": (C.c_int, [H, C.c_int, dp, dp, dp, dp]),
@@ -302,7 +305,8 @@ class PigsCuda:
     Path[2Nb+1][Np][dim], xend[2][dim], R[Np][dim]."""
 
     def __init__(self, cfg: dict, n_chains: int = 1, rng: str = "philox", seed: int | None = None, device: int = 0,
-                 threads_per_chain: int = 0, table_mode: int = -1):
+                 threads_per_chain: int = 0, table_mode: int = -1, schedule: int = -1, chain_offset: int = 0,
+                 gpus: int = 1):
         self.L = load_library()
         self.cfg = dict(cfg)
         self.geo = derive_geometry(cfg)
@@ -325,6 +329,7 @@ class PigsCuda:
         p.seed = int(cfg.get("seed", 1982) if seed is None else seed)
         p.device, p.threads_per_chain, p.table_mode = int(device), int(threads_per_chain), int(table_mode)
         p.action = 1 if str(cfg.get("action", "chin")).lower().startswith("prim") else 0
+        p.schedule, p.chain_offset, p.gpus = int(schedule), int(chain_offset), int(gpus)
         self.p = p
         self.dim, self.Np, self.Nb, self.Nmax = p.dim, p.Np, p.Nb, p.Nmax
         self.Nbin, self.Nk, self.Npw, self.n_chains = p.Nbin, p.Nk, p.Npw, p.n_chains
@@ -465,6 +470,31 @@ class PigsCuda:
         else:
             self._ck(self.L.pigs_get_block_chain(self.h, int(chain), C.byref(b), _dp(gr), _dp(Sk), _dp(nr)))
         return b.as_dict(), gr, Sk[:self.Nk], nr
+
+    def get_block_chains(self, chain0=0, n=None):
+        """per-chain results of the last block in one transfer: (dict of arrays [n], gr[n][Nbin], Sk[n][Nk][dim],
+        nrho[n][Nbin][Npw+1])"""
+        n = self.n_chains - chain0 if n is None else int(n)
+        out = (PigsBlockResult * n)()
+        gr = np.zeros((n, self.Nbin))
+        Sk = np.zeros((n, max(self.Nk, 1), self.dim))
+        nr = np.zeros((n, self.Nbin, self.Npw + 1))
+        self._ck(self.L.pigs_get_block_chains(self.h, int(chain0), n, out, _dp(gr), _dp(Sk), _dp(nr)))
+        d = {k: np.array([getattr(o, k) for o in out]) for k in _BLOCK_F + _BLOCK_I}
+        d["bead_updates"] = np.array([list(o.bead_updates) for o in out])
+        d["n_open_chains"] = np.array([o.n_open_chains for o in out])
+        return d, gr, Sk[:, :self.Nk], nr
+
+    def launch_plan(self):
+        v = [C.c_int() for _ in range(5)]
+        self._ck(self.L.pigs_launch_plan(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("threads_per_chain", "groups_per_cta", "grid", "team", "table_mode"), (x.value for x in v)))
+
+    def schedule_name(self):
+        p = self.launch_plan()
+        if self.p.rng_mode == PIGS_RNG_MT_REPLAY:
+            return f"reference order (MT19937 replay), {p['threads_per_chain']} threads per chain"
+        return ("team: 4 window workers per chain" if p["team"] else f"window order, {p['threads_per_chain']} threads per chain")
 
     def block_vector(self):
         """(device pointer, length in doubles) of the chain-summed accumulator vector"""

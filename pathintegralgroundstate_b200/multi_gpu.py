@@ -22,8 +22,9 @@ def shard_chains(n_total: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def chain_seed(seed: int, first_chain: int) -> int:
-    """Every chain c of the whole job draws from stream seed + c, whatever the
-    number of ranks: rank r seeds its local chain i with seed + first + i."""
+    """MT19937 replay only: rank r's local chain i is seeded with sgrnd(seed + first + i).  Prefer
+    PigsCuda(..., seed=seed, chain_offset=first): the library then mixes the GLOBAL chain index into both the Philox
+    stream and the MT seed, so chain c of the job draws the same numbers whatever the number of ranks."""
     return int(seed) + int(first_chain)
 
 

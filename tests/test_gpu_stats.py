@@ -1,0 +1,147 @@
+"""Statistical gate of the PRODUCTION path: the Philox kernel (window-ordered sweeps, one warp per chain and team
+mode) against the CPU oracle driven by the reference's MT19937, liquid He-4 N = 64 with the WORM ON.
+
+BASELINE.json north_star: "MC averages (E/N, g(r), OBDM tail) agree within 2 sigma".  Error bars are cross-chain
+standard errors (chains are independent, so no autocorrelation estimate enters); ratios (acceptance ratios,
+histogram fractions) use a jackknife over chains.  Seeds are fixed, so the outcome is deterministic.
+
+Both sides start from EQUILIBRATED configurations (the GPU equilibrates all chains, the oracle chains start from
+distinct GPU chains that are in the diagonal sector), so the comparison does not depend on how fast either
+dynamics relaxes -- only on both sampling the same distribution.
+"""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from oracle.pigs_oracle import Oracle
+from pathintegralgroundstate_b200 import PigsCuda
+from tests.common import C2, oracle_cfg, synthetic_path
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(C2, CWorm=0.5, Nobdm=5, Nbin=50, Nk=10)       # N = 64, 2M = 30, bisection, worm on, swap on
+N_ORC, N_EQ, N_MEAS = 32, 400, 240
+SIGMA = 2.0
+
+
+def jack(num, den):
+    """ratio of sums and its jackknife standard error over chains"""
+    num, den = np.asarray(num, float), np.asarray(den, float)
+    n = len(num)
+    R = num.sum() / den.sum()
+    loo = (num.sum() - num) / (den.sum() - den)
+    return R, np.sqrt((n - 1) / n * ((loo - loo.mean()) ** 2).sum())
+
+
+def observables(b, gr, nr, Np):
+    """per-chain numerators / denominators of every compared quantity: name -> (num[chain], den[chain])"""
+    o = {}
+    d = np.maximum(b["idiag_block"], 0).astype(float)
+    o["E/N mixed"] = (b["sumE"] / Np, d)
+    o["E/N thermodynamic"] = (b["sumEt"] / Np, d)
+    o["V/N"] = (b["sumV"] / Np, d)
+    ngr = b["ngr"].astype(float)
+    tot = gr.sum(axis=1)
+    peak = slice(24, 32)            # first peak of g(r): r ~ 1.35-1.8 sigma with rbin = rcut/50 = 0.056 sigma
+    o["g(r) first peak"] = (gr[:, peak].sum(axis=1), ngr)
+    o["g(r) r->L/2"] = (gr[:, -5:].sum(axis=1), ngr)
+    o["g(r) core edge"] = (gr[:, 15:20].sum(axis=1), ngr)
+    n0 = nr[:, :, 0]
+    o["n(r) tail r->L/2"] = (n0[:, -12:].sum(axis=1), n0.sum(axis=1))
+    o["n(r) r < 1 sigma"] = (n0[:, :18].sum(axis=1), n0.sum(axis=1))
+    for a, t in (("acc_cm", "try_cm"), ("acc_bd", "try_stag"), ("acc_head", "try_stag"), ("acc_tail", "try_stag"),
+                 ("acc_cm_half", "try_cm_half"), ("acc_bd_half", "try_stag_half"), ("acc_head_half", "try_stag_half"),
+                 ("acc_tail_half", "try_stag_half"), ("acc_open", "try_open"), ("acc_close", "try_close"),
+                 ("acc_swap", "try_swap")):
+        o["ratio " + a] = (b[a].astype(float), b[t].astype(float))
+    o["diagonal fraction"] = (d, np.full_like(d, float(N_MEAS)))
+    return o
+
+
+def _oracle_chain(args):
+    cfg, W, V, P, xe, seed = args
+    o = Oracle(oracle_cfg(cfg))
+    o.set_tables(W, V)
+    o.set_state(P, xe, 0, 0)
+    o.sgrnd(seed)
+    o.run_block(20)                                  # decorrelate from the hand-over configuration
+    b, gr, Sk, nr = o.run_block(N_MEAS)
+    return b, gr, nr
+
+
+@pytest.fixture(scope="module")
+def reference_side():
+    """the oracle's MT19937 chains, started from equilibrated diagonal configurations of a GPU run"""
+    g = PigsCuda(CFG, n_chains=512, rng="philox", seed=777, schedule=0)
+    g.fill_tables("hfdb")
+    rng = np.random.default_rng(11)
+    P0 = np.stack([synthetic_path(CFG, rng, spread=0.03) for _ in range(8)])
+    P = P0[np.arange(512) % 8]
+    xe = np.stack([np.stack([p[CFG["Nb"], -1]] * 2) for p in P])
+    g.set_state_all(P, xe)
+    g.run_block(N_EQ)
+    Pg, xg, io, iw = g.get_state_all()
+    closed = np.flatnonzero(io == 0)[:N_ORC]
+    assert len(closed) == N_ORC
+    o = Oracle(oracle_cfg(CFG))
+    o.fill_tables()
+    W, V = o.get_tables()
+    jobs = [(CFG, W, V, Pg[c], np.stack([Pg[c][CFG["Nb"], -1]] * 2), 9000 + i) for i, c in enumerate(closed)]
+    with ThreadPoolExecutor(max_workers=min(N_ORC, os.cpu_count() or 4)) as ex:
+        res = list(ex.map(_oracle_chain, jobs))      # ctypes releases the GIL: one chain per host core
+    b = {k: np.array([r[0][k] for r in res]) for k in res[0][0] if k != "bead_updates"}
+    gr = np.stack([r[1] for r in res])
+    nr = np.stack([r[2] for r in res])
+    g.close()
+    return observables(b, gr, nr, CFG["Np"]), (Pg, xg, io, iw)
+
+
+def gpu_side(schedule, n_chains, start):
+    Pg, xg, io, iw = start
+    g = PigsCuda(CFG, n_chains=n_chains, rng="philox", seed=4242 + schedule, schedule=schedule)
+    g.fill_tables("hfdb")
+    idx = np.flatnonzero(io == 0)
+    idx = idx[np.arange(n_chains) % len(idx)]
+    g.set_state_all(Pg[idx], np.stack([np.stack([Pg[c][CFG["Nb"], -1]] * 2) for c in idx]))
+    g.run_block(60)                                  # chains started from the same configuration drift apart
+    g.run_block(N_MEAS)
+    b, gr, Sk, nr = g.get_block_chains()
+    g.close()
+    return observables(b, gr, nr, CFG["Np"])
+
+
+def compare(og, oo, names):
+    report, bad = [], []
+    for name in names:
+        Rg, sg = jack(*og[name])
+        Ro, so = jack(*oo[name])
+        z = (Rg - Ro) / np.hypot(sg, so)
+        report.append(f"{name:24s} gpu {Rg: .6f} +- {sg:.6f}   oracle {Ro: .6f} +- {so:.6f}   z = {z:+.2f}")
+        if not abs(z) <= SIGMA:
+            bad.append(name)
+    print("\n".join(report))
+    assert not bad, "outside 2 sigma: " + ", ".join(bad) + "\n" + "\n".join(report)
+
+
+ENERGY_AND_STRUCTURE = ["E/N mixed", "E/N thermodynamic", "V/N", "g(r) first peak", "g(r) r->L/2", "g(r) core edge",
+                        "n(r) tail r->L/2", "n(r) r < 1 sigma", "diagonal fraction"]
+RATIOS = ["ratio " + a for a in ("acc_cm", "acc_bd", "acc_head", "acc_tail", "acc_cm_half", "acc_bd_half", "acc_head_half",
+                                 "acc_tail_half", "acc_open", "acc_close", "acc_swap")]
+
+
+def test_philox_windowed_matches_oracle_within_2_sigma(reference_side):
+    """schedule 0: one warp per chain walks the windows of a pass one after the other (the benchmarked kernel)"""
+    oo, start = reference_side
+    og = gpu_side(0, 2048, start)
+    compare(og, oo, ENERGY_AND_STRUCTURE + RATIOS)
+
+
+def test_philox_team_matches_oracle_within_2_sigma(reference_side):
+    """schedule 1: four warps per chain sweep four disjoint windows at once (few chains per GPU).  A team pass makes
+    two middle sweeps (acc_bd / try_stag is therefore not the reference's ratio) and draws the middle windows
+    between the end windows, so only the physics is compared, not the per-move acceptance of the middle move."""
+    oo, start = reference_side
+    og = gpu_side(1, 1024, start)
+    compare(og, oo, ENERGY_AND_STRUCTURE + [r for r in RATIOS if r not in ("ratio acc_bd",)])
