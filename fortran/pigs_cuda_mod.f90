@@ -32,7 +32,7 @@ type, bind(C) :: pigs_params
    integer(c_int32_t) :: n_chains, rng_mode
    integer(c_int64_t) :: seed
    integer(c_int32_t) :: device, threads_per_chain, table_mode, action
-   integer(c_int32_t) :: schedule = -1, chain_offset = 0, gpus = 1
+   integer(c_int32_t) :: schedule, chain_offset, gpus      ! -1 / 0 / 1 for the reference's single-GPU, single-run use
 end type pigs_params
 
 ! struct pigs_block_result
@@ -194,6 +194,48 @@ interface
      real(c_double), intent(inout) :: nrho(*)
      integer(c_int)                :: rc
    end function pigs_obdm
+
+   ! MT19937 state of one chain (mtsavef / mtgetf, random_mod.f90:125-191)
+   function pigs_get_mt(h, chain, mt624, mti) bind(C, name='pigs_get_mt') result(rc)
+     import :: c_int, c_ptr, c_int32_t
+     type(c_ptr), value              :: h
+     integer(c_int), value           :: chain
+     integer(c_int32_t), intent(out) :: mt624(*), mti
+     integer(c_int)                  :: rc
+   end function pigs_get_mt
+
+   function pigs_set_mt(h, chain, mt624, mti) bind(C, name='pigs_set_mt') result(rc)
+     import :: c_int, c_ptr, c_int32_t
+     type(c_ptr), value             :: h
+     integer(c_int), value          :: chain
+     integer(c_int32_t), intent(in) :: mt624(*)
+     integer(c_int32_t), value      :: mti
+     integer(c_int)                 :: rc
+   end function pigs_set_mt
+
+   ! n draws of the chain's grnd() stream (random_mod.f90:35-115), e.g. for init's starting positions
+   function pigs_grnd(h, chain, n, u) bind(C, name='pigs_grnd') result(rc)
+     import :: c_int, c_ptr, c_double
+     type(c_ptr), value          :: h
+     integer(c_int), value       :: chain, n
+     real(c_double), intent(out) :: u(*)
+     integer(c_int)              :: rc
+   end function pigs_grnd
+
+   ! every chain's complete state in one binary file (what CheckPoint + mtsavef do for one chain)
+   function pigs_save_checkpoint(h, path) bind(C, name='pigs_save_checkpoint') result(rc)
+     import :: c_int, c_ptr, c_char
+     type(c_ptr), value                 :: h
+     character(kind=c_char), intent(in) :: path(*)      ! NUL-terminated
+     integer(c_int)                     :: rc
+   end function pigs_save_checkpoint
+
+   function pigs_load_checkpoint(h, path) bind(C, name='pigs_load_checkpoint') result(rc)
+     import :: c_int, c_ptr, c_char
+     type(c_ptr), value                 :: h
+     character(kind=c_char), intent(in) :: path(*)
+     integer(c_int)                     :: rc
+   end function pigs_load_checkpoint
 
 end interface
 

@@ -185,6 +185,15 @@ int  pigs_launch_count(pigs_handle h, int64_t* n);
  * smem, 3 trap) */
 int  pigs_launch_plan(pigs_handle h, int* threads_per_chain, int* groups_per_cta, int* grid, int* team, int* table_mode);
 
+/* ---- multi-chain checkpoint (what the reference lacks) -------------------------------------------------------
+ * The reference saves ONE chain as text (CheckPoint, vpi_mod.f90:263-309) plus its MT19937 state (mtsavef,
+ * random_mod.f90:125-158), and loses every accumulator on restart; the drivers keep writing that pair for chain 0.
+ * These two calls save / restore the complete device state of EVERY chain (paths, xend, worm and permutation
+ * bookkeeping, Philox counters, MT19937 states) in one binary file in global chain order, so a run resumes bit for
+ * bit -- also on a different number of GPUs.  The drivers add their own accumulators in checkpoint_driver.bin. */
+int  pigs_save_checkpoint(pigs_handle h, const char* path);
+int  pigs_load_checkpoint(pigs_handle h, const char* path);
+
 /* ---- unit API: one reference procedure per call, applied to EVERY chain's
  * device state with that chain's own random stream ---- */
 /* any of the 14 moves (PIGS_* above) for particle ip (1-based; for PIGS_SWAP the

@@ -556,6 +556,111 @@ extern "C" int pigs_set_perm(pigs_handle h, int chain, int iperm, const int32_t*
     return PIGS_OK;
 }
 
+// ---- multi-chain checkpoint ---------------------------------------------------------------------
+// The reference checkpoints ONE chain as text (CheckPoint, vpi_mod.f90:263-309) and its RNG state (mtsavef,
+// random_mod.f90:125-158); the driver keeps writing those for chain 0.  This is the extension SURVEY 8(f2) asks
+// for: every chain's path, xend, worm / permutation state, Philox counters and MT19937 state in one binary file,
+// in GLOBAL chain order, so a run can be resumed on a different number of GPUs.  Little-endian, version 1:
+//   "PIGSCKP1" | int32 dim, Np, Nb, n_chains, rng_mode, PCS, IS_N, reserved | uint64 seed |
+//   Path[n][2Nb+1][Np][dim] f64 | xend[n][2][dim] f64 | istate[n][IS_N] i32 | cyc[n][Np] i32 | hist[n][Np] i32 |
+//   pctr[n][PCS] u64 | mt[n][624] u32
+static const char CKP_MAGIC[8] = {'P', 'I', 'G', 'S', 'C', 'K', 'P', '1'};
+struct CkpHeader {
+    char magic[8];
+    int32_t dim, Np, Nb, n_chains, rng_mode, pcs, is_n, reserved;
+    uint64_t seed;
+};
+template <class T>
+static int ckp_array(pigs_ctx* h, FILE* f, bool save, T* dptr, size_t per_chain) {
+    std::vector<T> buf((size_t)h->hp.n_chains * per_chain);
+    if (save) {
+        CK(cudaMemcpyAsync(buf.data(), dptr, buf.size() * sizeof(T), cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        if (fwrite(buf.data(), sizeof(T), buf.size(), f) != buf.size()) return fail(PIGS_E_STATE, "checkpoint: short write");
+    } else {
+        if (fread(buf.data(), sizeof(T), buf.size(), f) != buf.size()) return fail(PIGS_E_STATE, "checkpoint: short read");
+        CK(cudaMemcpyAsync(dptr, buf.data(), buf.size() * sizeof(T), cudaMemcpyHostToDevice, h->st));
+        CK(cudaStreamSynchronize(h->st));
+    }
+    return PIGS_OK;
+}
+static int ckp_paths(pigs_ctx* h, FILE* f, bool save) {
+    const DevParams& P = h->P;
+    const size_t per = (size_t)P.S * P.Np * P.dim;
+    std::vector<double> buf((size_t)h->hp.n_chains * per), xe((size_t)h->hp.n_chains * 2 * P.dim);
+    std::vector<int32_t> io(h->hp.n_chains), iw(h->hp.n_chains);
+    if (save) {
+        int rc = get_paths(h, 0, h->hp.n_chains, buf.data());
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(h->st));
+        if (fwrite(buf.data(), sizeof(double), buf.size(), f) != buf.size()) return fail(PIGS_E_STATE, "checkpoint: short write");
+    } else {
+        if (fread(buf.data(), sizeof(double), buf.size(), f) != buf.size()) return fail(PIGS_E_STATE, "checkpoint: short read");
+        int rc = put_paths(h, 0, h->hp.n_chains, buf.data());
+        if (rc) return rc;
+    }
+    return PIGS_OK;
+}
+// one pass over the file per array, shard after shard: the file is in global chain order
+static int ckp_io(pigs_ctx* h, const char* path, bool save) {
+    if (!path) return fail(PIGS_E_ARG, "null path");
+    std::vector<pigs_ctx*> parts = h->sub.empty() ? std::vector<pigs_ctx*>{h} : h->sub;
+    for (pigs_ctx* s : parts) { CK(cudaSetDevice(s->hp.device)); CK(cudaStreamSynchronize(s->st)); }
+    FILE* f = fopen(path, save ? "wb" : "rb");
+    if (!f) return fail(PIGS_E_STATE, std::string("cannot open ") + path);
+    CkpHeader H;
+    std::memset(&H, 0, sizeof H);
+    const pigs_params& p = h->hp;
+    int rc = PIGS_OK;
+    if (save) {
+        std::memcpy(H.magic, CKP_MAGIC, 8);
+        H.dim = p.dim; H.Np = p.Np; H.Nb = p.Nb; H.n_chains = p.n_chains; H.rng_mode = p.rng_mode; H.pcs = PCS; H.is_n = IS_N;
+        H.seed = p.seed;
+        if (fwrite(&H, sizeof H, 1, f) != 1) rc = fail(PIGS_E_STATE, "checkpoint: short write");
+    } else {
+        if (fread(&H, sizeof H, 1, f) != 1 || std::memcmp(H.magic, CKP_MAGIC, 8) != 0) rc = fail(PIGS_E_STATE, "not a PIGSCKP1 checkpoint");
+        else if (H.dim != p.dim || H.Np != p.Np || H.Nb != p.Nb || H.n_chains != p.n_chains || H.rng_mode != p.rng_mode || H.pcs != PCS || H.is_n != IS_N)
+            rc = fail(PIGS_E_ARG, "checkpoint was written for another configuration (dim, Np, Nb, n_chains or rng_mode differ)");
+    }
+    for (int arr = 0; arr < 7 && rc == PIGS_OK; ++arr)
+        for (pigs_ctx* s : parts) {
+            if (cudaSetDevice(s->hp.device) != cudaSuccess) { rc = fail(PIGS_E_CUDA, "cudaSetDevice"); break; }
+            const DevParams& P = s->P;
+            switch (arr) {
+            case 0: rc = ckp_paths(s, f, save); break;
+            case 1: {       // xend travels as [2][dim] like the ABI, the device keeps [2][3]
+                std::vector<double> x6((size_t)s->hp.n_chains * 6, 0.0), xd((size_t)s->hp.n_chains * 2 * P.dim);
+                if (save) {
+                    if (cudaMemcpy(x6.data(), s->d_xend, x6.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail(PIGS_E_CUDA, "xend copy"); break; }
+                    for (int c = 0; c < s->hp.n_chains; ++c) for (int j = 0; j < 2; ++j) for (int k = 0; k < P.dim; ++k) xd[((size_t)c * 2 + j) * P.dim + k] = x6[(size_t)c * 6 + j * 3 + k];
+                    if (fwrite(xd.data(), 8, xd.size(), f) != xd.size()) rc = fail(PIGS_E_STATE, "checkpoint: short write");
+                } else {
+                    if (fread(xd.data(), 8, xd.size(), f) != xd.size()) { rc = fail(PIGS_E_STATE, "checkpoint: short read"); break; }
+                    for (int c = 0; c < s->hp.n_chains; ++c) for (int j = 0; j < 2; ++j) for (int k = 0; k < P.dim; ++k) x6[(size_t)c * 6 + j * 3 + k] = xd[((size_t)c * 2 + j) * P.dim + k];
+                    if (cudaMemcpy(s->d_xend, x6.data(), x6.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(PIGS_E_CUDA, "xend copy");
+                }
+                break;
+            }
+            case 2: rc = ckp_array(s, f, save, s->d_istate, (size_t)IS_N); break;
+            case 3: rc = ckp_array(s, f, save, s->d_cyc, (size_t)P.Np); break;
+            case 4: rc = ckp_array(s, f, save, s->d_hist, (size_t)P.Np); break;
+            case 5: rc = ckp_array(s, f, save, s->d_pctr, (size_t)PCS); break;
+            case 6: rc = ckp_array(s, f, save, s->d_mt, (size_t)624); break;
+            }
+            if (rc != PIGS_OK) break;
+        }
+    fclose(f);
+    return rc;
+}
+extern "C" int pigs_save_checkpoint(pigs_handle h, const char* path) {
+    if (!h) return fail(PIGS_E_ARG, "null handle");
+    return ckp_io(h, path, true);
+}
+extern "C" int pigs_load_checkpoint(pigs_handle h, const char* path) {
+    if (!h) return fail(PIGS_E_ARG, "null handle");
+    return ckp_io(h, path, false);
+}
+
 // ---- random streams ----------------------------------------------------------------------------
 extern "C" int pigs_sgrnd(pigs_handle h, int chain, int32_t seed) {
     if (h && !h->sub.empty()) {

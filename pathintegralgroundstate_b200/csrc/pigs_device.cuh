@@ -143,7 +143,8 @@ struct GS {
     // Geometry of the thread group that currently works on this block (set by thread 0 of the owner, read after a
     // sync): normally the chain group of T threads; in team mode one warp (a window worker) during the sweeps.
     int gsize, gshift, gbar;
-    int pad0, pad1, pad2;
+    // windows of the current pass of the window-ordered sweep (win_sweep): head / tail lengths, middle starts
+    int wLh, wLt, wM0, wM1, wnM;
     MovePark pk;
     // followed by: seg_old[3S] seg_new[3S] part[np*8] pp[Np]
 };
@@ -151,9 +152,12 @@ struct GS {
 struct Grp {
     int tid, lane, warp, nwarps, size;
 };
+// the size of the group working on block gs: with one warp per chain (the production shape) it is a launch
+// constant -- no shared-memory read on the serial path of a move (measured: -8 % at N = 64 when every sync looked it up)
+__device__ __forceinline__ int gsize_of(const GS* gs) { return cA.threads_per_chain == 32 ? 32 : gs->gsize; }
 __device__ __forceinline__ Grp grp(const GS* gs) {
     Grp g;
-    g.size = gs->gsize;
+    g.size = gsize_of(gs);
     g.tid = threadIdx.x & (g.size - 1);
     g.lane = threadIdx.x & 31;
     g.warp = g.tid >> 5;
@@ -161,6 +165,7 @@ __device__ __forceinline__ Grp grp(const GS* gs) {
     return g;
 }
 __device__ __forceinline__ void gsync(const GS* gs) {
+    if (cA.threads_per_chain == 32) { __syncwarp(); return; }
     const int n = gs->gsize;
     if (n == 32) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(gs->gbar), "r"(n) : "memory");
@@ -170,7 +175,7 @@ __device__ __forceinline__ void tsync() {
     if (cA.threads_per_chain == 32) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x >> cA.tshift)), "r"(cA.threads_per_chain) : "memory");
 }
-__device__ __forceinline__ bool gfirst(const GS* gs) { return (threadIdx.x & (gs->gsize - 1)) == 0; }
+__device__ __forceinline__ bool gfirst(const GS* gs) { return (threadIdx.x & (gsize_of(gs) - 1)) == 0; }
 __host__ __device__ inline int part_slots(int nwarps) { return nwarps < 4 ? 4 : nwarps; }
 __host__ __device__ inline size_t grp_smem_bytes(int S, int Np, int nwarps) {
     return sizeof(GS) + sizeof(double) * ((size_t)6 * S + (size_t)part_slots(nwarps) * 8 + (size_t)Np);

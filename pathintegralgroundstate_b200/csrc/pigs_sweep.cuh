@@ -449,7 +449,7 @@ PIGS_T __device__ __forceinline__ void TranslateHalfChain(GS* gs, ull* pctr, int
     // cut bead at full weight (Q21)
     if (run_move<MT, VAR>(gs, pctr, MV_TRANSLATE | (half << 2), ip0, ibi, ibf, ibi, ibf, 0.0)) {
         bump(gs, C_ACC_CM_HALF);
-        const int t = threadIdx.x & (gs->gsize - 1);
+        const int t = threadIdx.x & (gsize_of(gs) - 1);
         if (t < cP.dim) gs->xend[(half - 1) * 3 + t] = sn(gs, t, cP.Nb);
         gsync(gs);
     }
@@ -477,7 +477,7 @@ PIGS_T __device__ __forceinline__ void MoveHead(GS* gs, ull* pctr, int Lmax, int
     if (run_move<MT, VAR>(gs, pctr, fl, ip0, ii, ie, ii, ie - 1, 0.0)) {
         bump(gs, half ? C_ACC_HEAD_HALF : C_ACC_HEAD);
         if (half == 2) {       // the free end IS the cut bead
-            const int t = threadIdx.x & (gs->gsize - 1);
+            const int t = threadIdx.x & (gsize_of(gs) - 1);
             if (t < cP.dim) gs->xend[3 + t] = sn(gs, t, cP.Nb);
             gsync(gs);
         }
@@ -493,7 +493,7 @@ PIGS_T __device__ __forceinline__ void MoveTail(GS* gs, ull* pctr, int Lmax, int
     if (run_move<MT, VAR>(gs, pctr, fl, ip0, ii, ie, ii + 1, ie, 0.0)) {
         bump(gs, half ? C_ACC_TAIL_HALF : C_ACC_TAIL);
         if (half == 1) {
-            const int t = threadIdx.x & (gs->gsize - 1);
+            const int t = threadIdx.x & (gsize_of(gs) - 1);
             if (t < cP.dim) gs->xend[t] = sn(gs, t, cP.Nb);
             gsync(gs);
         }
@@ -520,7 +520,7 @@ PIGS_T __device__ __forceinline__ int draw_half(GS* gs, ull& ctr) { int h = (int
 
 // OpenChain (vpi_mod.f90:1821-2076) when open, CloseChain (:2080-2266) otherwise
 PIGS_T static __device__ __noinline__ void OpenClose(GS* gs, ull* pctr, int Lmax, int ip0, bool open) {
-    const int t = threadIdx.x & (gs->gsize - 1);
+    const int t = threadIdx.x & (gsize_of(gs) - 1);
     ull ctr = *pctr;
     int Ls = draw_even_Ls<MT, VAR>(gs, ctr, Lmax), half = draw_half<MT, VAR>(gs, ctr);
     *pctr = ctr;
@@ -1018,8 +1018,6 @@ __device__ __forceinline__ void win_sweep(GS* gs0, GS* gsw, ull* pctr, ull* pwct
     const int rot = team ? wk * (Np >> 2) : 0;                   // rotated particle order of worker wk
     const int total = nT + cP.Nstag * nsub * Np;
     int sub = 0, k = 0, left = 0;       // position inside the pass; moves left until the next team barrier
-    WinPass wp;
-    wp.Lh = wp.Lt = 2; wp.iiM[0] = wp.iiM[1] = 0; wp.nM = 0;
     for (int q = 0; q < total; ++q) {
         GS* g;
         ull* rs;
@@ -1040,8 +1038,11 @@ __device__ __forceinline__ void win_sweep(GS* gs0, GS* gsw, ull* pctr, ull* pwct
                     }
                 }
                 ull c = *pctr;
-                wp = draw_pass<VAR>(gsw, c, team);
+                const WinPass wp = draw_pass<VAR>(gsw, c, team);
                 *pctr = c;
+                // parked in the worker's block (every thread writes the same values and reads back its own): nothing of
+                // the pass stays in registers across the move engine
+                gsw->wLh = wp.Lh; gsw->wLt = wp.Lt; gsw->wM0 = wp.iiM[0]; gsw->wM1 = wp.iiM[1]; gsw->wnM = wp.nM;
                 left = 0;
             }
             if (team && left == 0) { tsync(); left = chunk; }
@@ -1055,13 +1056,13 @@ __device__ __forceinline__ void win_sweep(GS* gs0, GS* gsw, ull* pctr, ull* pwct
             const bool head = cs == 0, tail = team ? cs == 3 : cs == 1;
             if (head) {                 // MoveHead / MoveHeadBisection
                 bump(g, C_TRY_STAG);
-                flags = ty | MV_FREE_NEXT; ii = 0; ie = wp.Lh; m0 = 0; m1 = ie - 1; cacc = C_ACC_HEAD;
+                flags = ty | MV_FREE_NEXT; ii = 0; ie = g->wLh; m0 = 0; m1 = ie - 1; cacc = C_ACC_HEAD;
             } else if (tail) {          // MoveTail / MoveTailBisection
-                flags = ty | MV_FREE_PREV; ie = twoNb; ii = ie - wp.Lt; m0 = ii + 1; m1 = ie; cacc = C_ACC_TAIL;
+                flags = ty | MV_FREE_PREV; ie = twoNb; ii = ie - g->wLt; m0 = ii + 1; m1 = ie; cacc = C_ACC_TAIL;
             } else {                    // Staging / Bisection
                 const int j = team ? cs - 1 : 0;
-                if (j >= wp.nM) continue;
-                flags = ty; ii = wp.iiM[j]; ie = ii + Lm; m0 = ii + 1; m1 = ie - 1; cacc = C_ACC_BD;
+                if (j >= g->wnM) continue;
+                flags = ty; ii = j ? g->wM1 : g->wM0; ie = ii + Lm; m0 = ii + 1; m1 = ie - 1; cacc = C_ACC_BD;
             }
         }
         if (run_move_body<false, VAR>(g, rs, flags, ip, ii, ie, m0, m1, 0.0)) bump(g, cacc);

@@ -51,6 +51,11 @@ std::string fmt_f(double x, int d) {
 }
 // Fw.d
 std::string fortran_f(double x, int w, int d) {
+    if (std::isnan(x)) return rjust("NaN", w);             // gfortran's spelling of non-finite values
+    if (std::isinf(x)) {
+        const std::string t = x > 0 ? (w >= 8 ? "Infinity" : "Inf") : (w >= 9 ? "-Infinity" : "-Inf");
+        return (int)t.size() <= w ? rjust(t, w) : std::string(w, '*');
+    }
     std::string s = fmt_f(x, d);
     if (d == 0) s += ".";                                  // Fortran always prints the decimal point
     if (s.rfind("0.", 0) == 0 && (int)s.size() > w) s = s.substr(1);
@@ -245,12 +250,18 @@ struct Config {
     double Rm = 0;
     std::vector<double> a_ho;
     // &cuda (not in the reference)
-    int n_chains = 1, threads_per_chain = 0, table_mode = -1, schedule = -1;
+    int n_chains = 1, threads_per_chain = 0, table_mode = -1, schedule = -1, gpus = 1, checkpoint_every = 1;
     std::string rng, action;
     // crystal: config_ini.in line 2
     std::vector<double> Lbox_in;
 };
 
+bool file_exists(const std::string& p) {
+    FILE* f = fopen(p.c_str(), "rb");
+    if (f) fclose(f);
+    return f != nullptr;
+}
+void die(const std::string& msg);
 void die(const std::string& msg) {
     std::cerr << "vpi_cuda: " << msg << std::endl;
     std::exit(2);
@@ -292,6 +303,7 @@ Config read_vpi_in(const std::string& text) {
     }
     I("cuda", "n_chains", c.n_chains, false); I("cuda", "threads_per_chain", c.threads_per_chain, false);
     I("cuda", "table_mode", c.table_mode, false); I("cuda", "schedule", c.schedule, false);
+    I("cuda", "gpus", c.gpus, false); I("cuda", "checkpoint_every", c.checkpoint_every, false);
     if (const Value* v = get("cuda", "rng")) c.rng = lower(v->toks[0]);
     if (const Value* v = get("cuda", "action")) c.action = lower(v->toks[0]);      // 'chin' | 'primitive' (global_mod.f90:48,67)
     if (!missing.empty()) {
@@ -443,13 +455,22 @@ void say(const char* fmt, ...) {
     putchar('\n');
     fflush(stdout);
 }
-double pct(double a, double t) { return t != 0 ? 100.0 * a / t : std::nan(""); }
+// stdout of `program vpi` (vpi.f90:161-194, 552-586, 620-634): list-directed `print *` starts a record with one blank
+// and writes a default integer in 12 columns (gfortran); formats 101 (x,a,x,f7.2,x,a), 102 (a,x,G16.8e2,x,a,x,G16.8e2),
+// 103 (x,a,x,i5), 104 (x,a,x,G13.6e2), 105 (x,a,x,3G13.6e2).  Same lines as driver.py (tests compare them).
+double pct(double a, double t) { return t != 0 ? (double)(float)(100.0 * a) / t : std::nan(""); }                 // 100*real(acc)/try
+double pct2(double a, double t) { return t != 0 ? 100.0 * (double)(float)a / (double)(float)t : std::nan(""); }   // 100.d0*real(acc)/real(try)
+void ld(const std::string& text) { say("%s", (" " + text).c_str()); }
+void ldi(const std::string& text, long long v) { say(" %s%12lld", text.c_str(), v); }
+void f101(const std::string& text, double v, const char* tail) { say(" %s %s %s", text.c_str(), fortran_f(v, 7, 2).c_str(), tail); }
+void f102(const std::string& text, double a, double b) { say("%s %s +/- %s", text.c_str(), fortran_g(a, 16, 8, 2).c_str(), fortran_g(b, 16, 8, 2).c_str()); }
+void f103(const std::string& text, int v) { say(" %s %5d", text.c_str(), v); }
 
 }  // namespace
 
 int main(int argc, char** argv) {
     std::string workdir = ".", potential = "hfdb", rng_arg;
-    int chains_arg = 0, device = 0;
+    int chains_arg = 0, device = 0, gpus_arg = 0;
     bool tables_only = false, format_test = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
@@ -458,11 +479,12 @@ int main(int argc, char** argv) {
         else if (a == "--chains") chains_arg = std::atoi(next().c_str());
         else if (a == "--rng") rng_arg = next();
         else if (a == "--device") device = std::atoi(next().c_str());
+        else if (a == "--gpus") gpus_arg = std::atoi(next().c_str());
         else if (a == "--potential") potential = next();
         else if (a == "--tables-only") tables_only = true;
         else if (a == "--format-test") format_test = true;
         else if (a == "-h" || a == "--help") {
-            puts("usage: vpi_cuda [--workdir DIR] [--chains N] [--rng philox|mt] [--device D] [--potential hfdb|hfdhe2|zero]\n"
+            puts("usage: vpi_cuda [--workdir DIR] [--chains N] [--gpus G] [--rng philox|mt] [--device D] [--potential hfdb|hfdhe2|zero]\n"
                  "                [--tables-only] < vpi.in");
             return 0;
         } else die("unknown argument " + a);
@@ -537,7 +559,7 @@ int main(int argc, char** argv) {
     p.rng_mode = rng.rfind("mt", 0) == 0 ? PIGS_RNG_MT_REPLAY : PIGS_RNG_PHILOX;
     p.seed = (uint64_t)c.seed;
     p.device = device; p.threads_per_chain = c.threads_per_chain; p.table_mode = c.table_mode; p.action = c.action.rfind("prim", 0) == 0 ? 1 : 0;
-    p.schedule = c.schedule; p.chain_offset = 0;
+    p.schedule = c.schedule; p.chain_offset = 0; p.gpus = gpus_arg > 0 ? gpus_arg : c.gpus;
     pigs_handle h = nullptr;
     CK(pigs_create(&p, &h));
     CK(pigs_set_tables(h, W.data(), V.data()));
@@ -545,7 +567,13 @@ int main(int argc, char** argv) {
     // ---- init (vpi_mod.f90:149-259)
     std::vector<double> Path((size_t)S * Np * dim);
     double xend[6] = {0, 0, 0, 0, 0, 0};
-    if (c.resume) {
+    // resume = T with the extended checkpoint of an earlier run present: every chain and every accumulator comes
+    // back and the run continues at the next block (what the reference cannot do, Q10); else the reference's own
+    // resume: chain 0 from checkpoint.dat + rand_state, accumulators lost
+    const bool full_resume = c.resume && file_exists(P("checkpoint_chains.bin")) && file_exists(P("checkpoint_driver.bin"));
+    if (full_resume) {
+        CK(pigs_load_checkpoint(h, P("checkpoint_chains.bin").c_str()));
+    } else if (c.resume) {
         bool tr; int isopen, iworm;
         read_checkpoint(P("checkpoint.dat"), dim, Np, Nb, tr, isopen, iworm, Path, xend);
         std::vector<uint32_t> mt(624);
@@ -575,18 +603,28 @@ int main(int argc, char** argv) {
         }
     }
 
-    // ---- banner (vpi.f90:161-194), abridged: list-directed stdout is compiler-specific
+    // ---- banner (vpi.f90:161-194)
     const int Nblock = c.Nblock, Nstep = c.Nstep;
-    say("%s", "");
-    say(" ==============================================================");
-    say("                       VPI Monte Carlo                         ");
-    say(" ==============================================================");
-    say("   > Dimensions          : %5d", dim);
-    say("   > Number of particles : %5d", Np);
-    say("   > Number of beads     : %5d", Nb);
-    say("   > Number of blocks    : %5d", Nblock);
-    say("   > MC steps per block  : %5d", Nstep);
-    say("   > Markov chains (GPU) : %5d", n_chains);
+    {
+        const bool sta = lower(c.sampling).rfind("sta", 0) == 0;
+        ld(""); ld("=============================================================="); ld("                      VPI Monte Carlo                         ");
+        ld("=============================================================="); ld(""); ld(" ");
+        ld(std::string("# The Monte Carlo sampling will be performed using ") + (sta ? "STAGING" : "BISECTION")); ld("  algorithm");
+        ld(c.swapping ? "# The Monte Carlo sampling will use swap updates" : "# The Monte Carlo sampling will not use swap updates");
+        ld(" "); ld("# Simulation parameters:"); ld("");
+        f103("  > Dimensions          :", dim); f103("  > Number of particles :", Np);
+        auto g3 = [&](const double* v) { std::string t; for (int k = 0; k < dim; ++k) t += fortran_g(v[k], 13, 6, 2); return t; };
+        if (c.trap) say(" %s %s", "  > Trapping length     :", g3(g.a_ho).c_str());
+        else {
+            say(" %s %s", "  > Density             :", fortran_g(g.density, 13, 6, 2).c_str());
+            say(" %s %s", "  > Size of the box     :", g3(g.Lbox).c_str());
+        }
+        f103("  > Number of beads     :", Nb);
+        say(" %s %s", "  > Time step           :", fortran_g(c.dt, 13, 6, 2).c_str());
+        f103("  > Number of blocks    :", Nblock); f103("  > MC steps per block  :", Nstep);
+        if (n_chains > 1) f103("  > Markov chains (GPU) :", n_chains);      // not in the reference: the replicas run at once
+        ld("");
+    }
 
     std::vector<double> Av(6, 0.0), Av2(6, 0.0), AvGr(Nbin, 0.0), AvGr2(Nbin, 0.0), AvSk((size_t)Nk * dim, 0.0), AvSk2((size_t)Nk * dim, 0.0);
     std::vector<double> AvNr((size_t)Nbin * (Npw + 1), 0.0), AvNr2((size_t)Nbin * (Npw + 1), 0.0), nrho((size_t)Nbin * (Npw + 1), 0.0);
@@ -597,10 +635,37 @@ int main(int argc, char** argv) {
         nid[j] = g.density * k_n * (std::pow(rr[j] + 0.5 * g.rbin, dim) - std::pow(rr[j] - 0.5 * g.rbin, dim));
     }
     long long idiag_aux = 0;
-    int obdm_bl = 0, diag_bl = 0;
-    std::ofstream fe(P("e_vpi.out")), fet(P("et_vpi.out"));
-    const char* labs[6] = {"<E> ", "<Ec>", "<Ep>", "<Et>", "<Kt>", "<Vt>"};
-    for (int iblock = 1; iblock <= Nblock; ++iblock) {
+    int obdm_bl = 0, diag_bl = 0, iblock0 = 0;
+    // the driver's own state, in the order of checkpoint_driver.bin ("PIGSDRV1", count, doubles)
+    auto driver_state = [&](bool save) {
+        std::vector<std::vector<double>*> arrs = {&Av, &Av2, &AvGr, &AvGr2, &AvSk, &AvSk2, &AvNr, &AvNr2, &nrho};
+        size_t n = 4;
+        for (auto* a : arrs) n += a->size();
+        std::vector<double> v;
+        if (save) {
+            v = {(double)iblock0, (double)idiag_aux, (double)obdm_bl, (double)diag_bl};
+            for (auto* a : arrs) v.insert(v.end(), a->begin(), a->end());
+            FILE* f = fopen(P("checkpoint_driver.bin").c_str(), "wb");
+            if (!f) die("cannot write checkpoint_driver.bin");
+            const uint64_t cnt = v.size();
+            fwrite("PIGSDRV1", 1, 8, f); fwrite(&cnt, 8, 1, f); fwrite(v.data(), 8, v.size(), f);
+            fclose(f);
+        } else {
+            FILE* f = fopen(P("checkpoint_driver.bin").c_str(), "rb");
+            char mg[8]; uint64_t cnt = 0;
+            if (!f || fread(mg, 1, 8, f) != 8 || std::memcmp(mg, "PIGSDRV1", 8) != 0 || fread(&cnt, 8, 1, f) != 1 || cnt != n)
+                die("checkpoint_driver.bin does not belong to this configuration");
+            v.resize(n);
+            if (fread(v.data(), 8, n, f) != n) die("checkpoint_driver.bin is truncated");
+            fclose(f);
+            iblock0 = (int)v[0]; idiag_aux = (long long)v[1]; obdm_bl = (int)v[2]; diag_bl = (int)v[3];
+            size_t o = 4;
+            for (auto* a : arrs) { std::copy(v.begin() + o, v.begin() + o + a->size(), a->begin()); o += a->size(); }
+        }
+    };
+    if (full_resume) driver_state(false);
+    std::ofstream fe(P("e_vpi.out"), full_resume ? std::ios::app : std::ios::out), fet(P("et_vpi.out"), full_resume ? std::ios::app : std::ios::out);
+    for (int iblock = iblock0 + 1; iblock <= Nblock; ++iblock) {
         const auto t0 = std::chrono::steady_clock::now();
         CK(pigs_run_block(h, Nstep));
         pigs_block_result b;
@@ -661,21 +726,36 @@ int main(int argc, char** argv) {
             CK(pigs_get_mt(h, 0, mt.data(), &mti));
             append_rand_state(P("rand_state"), mt.data(), mti);
         }
+        // ... and the extended checkpoint: all chains (library) + the accumulators above (checkpoint_driver.bin)
+        if (c.checkpoint_every > 0 && (iblock % c.checkpoint_every == 0 || iblock == Nblock)) {
+            CK(pigs_save_checkpoint(h, P("checkpoint_chains.bin").c_str()));
+            iblock0 = iblock;
+            driver_state(true);
+        }
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        say(" -----------------------------------------------------------");
-        say(" BLOCK NUMBER : %d", iblock);
-        for (int i = 0; i < 6; ++i)
-            say("   > %s =%s +/-%s", labs[i], fortran_g(m[i] / Np, 16, 8, 2).c_str(), fortran_g(bvar[i] / Np, 16, 8, 2).c_str());
-        say(" > CM movements      = %7.2f %%", pct((double)b.acc_cm, (double)b.try_cm));
-        say(" > Staging movements = %7.2f %%", pct((double)b.acc_bd, (double)b.try_stag));
-        say(" > Head movements    = %7.2f %%", pct((double)b.acc_head, (double)b.try_stag));
-        say(" > Tail movements    = %7.2f %%", pct((double)b.acc_tail, (double)b.try_stag));
-        say(" > Diagonal conf.    = %7.2f %%", pct((double)nd, (double)Nstep * n_chains));
-        say(" > Open acc          = %7.2f %%", pct((double)b.acc_open, (double)b.try_open));
-        say(" > Close acc         = %7.2f %%", pct((double)b.acc_close, (double)b.try_close));
-        say(" > Swap acc          = %7.2f %%", pct((double)b.acc_swap, (double)b.try_swap));
-        say(" # Time per block    = %7.2f seconds   (%.4g bead-updates/s)", dt,
-            (double)(b.bead_updates[0] + b.bead_updates[1] + b.bead_updates[2]) / dt);
+        // the block report (vpi.f90:552-586)
+        ld("-----------------------------------------------------------"); ldi("BLOCK NUMBER :", iblock); ld(" "); ld("# Block results:"); ld(" ");
+        const char* lab2[6] = {"  > <E>  =", "  > <Ec> =", "  > <Ep> =", "  > <Et> =", "  > <Kt> =", "  > <Vt> ="};
+        for (int i = 0; i < 3; ++i) f102(lab2[i], m[i] / Np, bvar[i] / Np);
+        ld(" ");
+        for (int i = 3; i < 6; ++i) f102(lab2[i], m[i] / Np, bvar[i] / Np);
+        ld(""); ld("# Acceptance of diagonal movements:"); ld(" ");
+        f101("> CM movements      =", pct((double)b.acc_cm, (double)b.try_cm), "%");
+        f101("> Staging movements =", pct((double)b.acc_bd, (double)b.try_stag), "%");
+        f101("> Head movements    =", pct((double)b.acc_head, (double)b.try_stag), "%");
+        f101("> Tail movements    =", pct((double)b.acc_tail, (double)b.try_stag), "%");
+        ld(" "); ld("# Acceptance of off-diagonal movements:"); ld(" ");
+        f101("> CM movements      =", pct((double)b.acc_cm_half, (double)b.try_cm_half), "%");
+        f101("> Staging movements =", pct((double)b.acc_bd_half, (double)b.try_stag_half), "%");
+        f101("> Head movements    =", pct((double)b.acc_head_half, (double)b.try_stag_half), "%");
+        f101("> Tail movements    =", pct((double)b.acc_tail_half, (double)b.try_stag_half), "%");
+        ld(" "); ld("# Acceptance open/close updates:"); ld(" ");
+        f101("> Diagonal conf.    =", pct2((double)nd, (double)Nstep * n_chains), "%");
+        f101("> Open acc          =", pct2((double)b.acc_open, (double)b.try_open), "%");
+        f101("> Close acc         =", pct2((double)b.acc_close, (double)b.try_close), "%");
+        f101("> Swap acc          =", pct2((double)b.acc_swap, (double)b.try_swap), "%");
+        say("  "); f101("# Time per block    =", dt, "seconds");
+        say(" # GPU throughput    = %.4g bead-updates/s", (double)(b.bead_updates[0] + b.bead_updates[1] + b.bead_updates[2]) / dt);
     }
     fe.close();
     fet.close();
@@ -694,12 +774,14 @@ int main(int argc, char** argv) {
     }
     // finals (vpi.f90:606-642)
     if (diag_bl) {
-        say(" ==============================================================");
-        say(" FINAL RESULTS:");
+        ld("=============================================================="); ld("FINAL RESULTS:"); ld(""); ld("# Final averages:"); ld("");
+        const char* lab2[6] = {"  > <E>  =", "  > <Ec> =", "  > <Ep> =", "  > <Et> =", "  > <Kt> =", "  > <Vt> ="};
         for (int i = 0; i < 6; ++i) {
+            if (i == 3) ld("");
             const double A = Av[i] / diag_bl, A2 = Av2[i] / diag_bl;
-            say("   > %s =%s +/-%s", labs[i], fortran_g(A / Np, 16, 8, 2).c_str(), fortran_g(var(diag_bl, A, A2) / Np, 16, 8, 2).c_str());
+            f102(lab2[i], A / Np, var(diag_bl, A, A2) / Np);
         }
+        ld(""); ld("=============================================================="); ld("");
     }
     if (!c.trap && diag_bl) {
         {

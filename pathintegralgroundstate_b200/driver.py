@@ -32,7 +32,12 @@ from .host import derive_geometry, make_table, mcmillan_logpsi, aziz_hfdb, aziz_
 
 # ------------------------------------------------------------------ Fortran edit descriptors
 def fortran_f(x: float, w: int, d: int) -> str:
-    """Fw.d"""
+    """Fw.d (gfortran spells non-finite values NaN / Infinity, or Inf when the field is narrower than 8)"""
+    if math.isnan(x):
+        return "NaN".rjust(w)
+    if math.isinf(x):
+        t = ("Infinity" if w >= 8 else "Inf") if x > 0 else ("-Infinity" if w >= 9 else "-Inf")
+        return t.rjust(w) if len(t) <= w else "*" * w
     s = f"{x:.{d}f}"
     if d == 0:
         s += "."                       # Fortran always prints the decimal point
@@ -154,6 +159,87 @@ def read_rand_state(path):
 
 
 # ------------------------------------------------------------------ the driver
+# ------------------------------------------------------------------ stdout of `program vpi` (vpi.f90:161-194, 552-586, 620-634)
+# list-directed `print *` starts every record with one blank (gfortran) and writes a default integer in 12 columns;
+# formats 101-105 are the reference's: 101 (x,a,x,f7.2,x,a)  102 (a,x,G16.8e2,x,a,x,G16.8e2)  103 (x,a,x,i5)
+# 104 (x,a,x,G13.6e2)  105 (x,a,x,3G13.6e2).  Written from the Fortran 2003 rules; no gfortran exists here to diff against.
+def _ld(text="", ival=None):
+    return " " + text + ("" if ival is None else f"{ival:12d}")
+
+
+def _f101(text, val=None, tail=None):
+    return " " + text + ("" if val is None else " " + fortran_f(val, 7, 2) + " " + tail)
+
+
+def _f102(text, a, b):
+    return text + " " + fortran_g(a, 16, 8, 2) + " +/- " + fortran_g(b, 16, 8, 2)
+
+
+def banner_lines(cfg, geo, Nblock, Nstep, n_chains, schedule=None):
+    sta = str(cfg["sampling"]).strip().lower().startswith("sta")
+    out = [_ld(""), _ld("=============================================================="),
+           _ld("                      VPI Monte Carlo                         "),
+           _ld("=============================================================="), _ld(""), _ld(" "),
+           _ld("# The Monte Carlo sampling will be performed using " + ("STAGING" if sta else "BISECTION")), _ld("  algorithm"),
+           _ld("# The Monte Carlo sampling will use swap updates" if cfg.get("swapping") else
+               "# The Monte Carlo sampling will not use swap updates"),
+           _ld(" "), _ld("# Simulation parameters:"), _ld(""),
+           f" {'  > Dimensions          :'} {geo['dim']:5d}", f" {'  > Number of particles :'} {geo['Np']:5d}"]
+    if geo["trap"]:
+        out.append(" " + "  > Trapping length     :" + " " + "".join(fortran_g(a, 13, 6, 2) for a in geo["a_ho"][:geo["dim"]]))
+    else:
+        out.append(" " + "  > Density             :" + " " + fortran_g(geo["density"], 13, 6, 2))
+        out.append(" " + "  > Size of the box     :" + " " + "".join(fortran_g(a, 13, 6, 2) for a in geo["Lbox"][:geo["dim"]]))
+    out += [f" {'  > Number of beads     :'} {int(cfg['Nb']):5d}", " " + "  > Time step           :" + " " + fortran_g(float(cfg["dt"]), 13, 6, 2),
+            f" {'  > Number of blocks    :'} {Nblock:5d}", f" {'  > MC steps per block  :'} {Nstep:5d}"]
+    if n_chains > 1:        # not in the reference: the replicas this build runs at once
+        out.append(f" {'  > Markov chains (GPU) :'} {n_chains:5d}")
+    out.append(_ld(""))
+    return out
+
+
+def block_report_lines(iblock, m, bvar, b, Np, Nstep, n_chains, dt):
+    f32 = lambda x: float(np.float32(x))
+    pct = lambda a, t: (f32(100 * a) / t) if t else float("nan")                     # 100*real(acc)/try   (try is real(8))
+    pct2 = lambda a, t: (100.0 * f32(a) / f32(t)) if t else float("nan")             # 100.d0*real(acc)/real(try)
+    out = [_ld("-----------------------------------------------------------"), _ld("BLOCK NUMBER :", iblock), _ld(" "),
+           _ld("# Block results:"), _ld(" ")]
+    for lab, i in (("  > <E>  =", 0), ("  > <Ec> =", 1), ("  > <Ep> =", 2)):
+        out.append(_f102(lab, m[i] / Np, bvar[i] / Np))
+    out.append(_ld(" "))
+    for lab, i in (("  > <Et> =", 3), ("  > <Kt> =", 4), ("  > <Vt> =", 5)):
+        out.append(_f102(lab, m[i] / Np, bvar[i] / Np))
+    out += [_ld(""), _ld("# Acceptance of diagonal movements:"), _ld(" "),
+            _f101("> CM movements      =", pct(b["acc_cm"], b["try_cm"]), "%"),
+            _f101("> Staging movements =", pct(b["acc_bd"], b["try_stag"]), "%"),
+            _f101("> Head movements    =", pct(b["acc_head"], b["try_stag"]), "%"),
+            _f101("> Tail movements    =", pct(b["acc_tail"], b["try_stag"]), "%"),
+            _ld(" "), _ld("# Acceptance of off-diagonal movements:"), _ld(" "),
+            _f101("> CM movements      =", pct(b["acc_cm_half"], b["try_cm_half"]), "%"),
+            _f101("> Staging movements =", pct(b["acc_bd_half"], b["try_stag_half"]), "%"),
+            _f101("> Head movements    =", pct(b["acc_head_half"], b["try_stag_half"]), "%"),
+            _f101("> Tail movements    =", pct(b["acc_tail_half"], b["try_stag_half"]), "%"),
+            _ld(" "), _ld("# Acceptance open/close updates:"), _ld(" "),
+            _f101("> Diagonal conf.    =", pct2(b["idiag_block"], Nstep * n_chains), "%"),
+            _f101("> Open acc          =", pct2(b["acc_open"], b["try_open"]), "%"),
+            _f101("> Close acc         =", pct2(b["acc_close"], b["try_close"]), "%"),
+            _f101("> Swap acc          =", pct2(b["acc_swap"], b["try_swap"]), "%"),
+            _f101(" "), _f101("# Time per block    =", dt, "seconds"),
+            f" # GPU throughput    = {sum(b['bead_updates']) / dt:.4g} bead-updates/s"]
+    return out
+
+
+def final_lines(A, V, Np):
+    out = [_ld("=============================================================="), _ld("FINAL RESULTS:"), _ld(""), _ld("# Final averages:"), _ld("")]
+    for lab, i in (("  > <E>  =", 0), ("  > <Ec> =", 1), ("  > <Ep> =", 2)):
+        out.append(_f102(lab, A[i] / Np, V[i] / Np))
+    out.append(_ld(""))
+    for lab, i in (("  > <Et> =", 3), ("  > <Kt> =", 4), ("  > <Vt> =", 5)):
+        out.append(_f102(lab, A[i] / Np, V[i] / Np))
+    out += [_ld(""), _ld("=============================================================="), _ld("")]
+    return out
+
+
 class VpiDriver:
     def __init__(self, cfg: dict, backend, workdir: str = ".", potential: str = "hfdb", quiet: bool = False):
         self.cfg, self.be, self.wd, self.quiet = dict(cfg), backend, workdir, quiet
@@ -196,6 +282,12 @@ class VpiDriver:
         c, g, be = self.cfg, self.geo, self.be
         dim, Np, Nb = g["dim"], g["Np"], int(c["Nb"])
         S = 2 * Nb + 1
+        self.full_resume = bool(c.get("resume")) and hasattr(be, "load_checkpoint") and \
+            os.path.exists(self._p("checkpoint_chains.bin")) and os.path.exists(self._p("checkpoint_driver.bin"))
+        if self.full_resume:
+            # the extended checkpoint of an earlier run: every chain (library) and every accumulator (run())
+            be.load_checkpoint(self._p("checkpoint_chains.bin"))
+            return
         if c.get("resume"):
             trap, isopen, iworm, Path, xend = read_checkpoint(self._p("checkpoint.dat"), dim, Np, Nb)
             mt, mti = read_rand_state(self._p("rand_state"))
@@ -229,17 +321,8 @@ class VpiDriver:
         density, rbin = g["density"], g["rbin"]
         self.tables()
         self.init_state()
-        # banner (vpi.f90:161-194), abridged: list-directed stdout is compiler-specific
-        self.say("")
-        self.say(" ==============================================================")
-        self.say("                       VPI Monte Carlo                         ")
-        self.say(" ==============================================================")
-        self.say(f"   > Dimensions          : {dim:5d}")
-        self.say(f"   > Number of particles : {Np:5d}")
-        self.say(f"   > Number of beads     : {Nb:5d}")
-        self.say(f"   > Number of blocks    : {Nblock:5d}")
-        self.say(f"   > MC steps per block  : {Nstep:5d}")
-        self.say(f"   > Markov chains (GPU) : {self.n_chains:5d}")
+        for ln in banner_lines(c, g, Nblock, Nstep, self.n_chains):      # vpi.f90:161-194
+            self.say(ln)
         Av = np.zeros(6)
         Av2 = np.zeros(6)
         AvGr, AvGr2 = np.zeros(Nbin), np.zeros(Nbin)
@@ -250,10 +333,37 @@ class VpiDriver:
         k_n = kn_ball(dim)
         rr = (np.arange(1, Nbin + 1, dtype=np.float64) - 0.5) * rbin
         nid = density * k_n * ((rr + 0.5 * rbin) ** dim - (rr - 0.5 * rbin) ** dim)
-        fe = open(self._p("e_vpi.out"), "w")
-        fet = open(self._p("et_vpi.out"), "w")
+        iblock0 = 0
+        arrs = [Av, Av2, AvGr, AvGr2, AvSk, AvSk2, AvNr, AvNr2, nrho]
+
+        def driver_state(save):
+            # checkpoint_driver.bin: "PIGSDRV1", uint64 count, doubles [iblock, idiag_aux, obdm_bl, diag_bl, Av, Av2, AvGr,
+            # AvGr2, AvSk, AvSk2, AvNr, AvNr2, nrho] -- the same file the compiled driver (csrc/vpi_main.cpp) writes
+            nonlocal iblock0, idiag_aux, obdm_bl, diag_bl
+            n = 4 + sum(a.size for a in arrs)
+            if save:
+                v = np.concatenate([[iblock0, idiag_aux, obdm_bl, diag_bl]] + [a.ravel() for a in arrs]).astype("<f8")
+                with open(self._p("checkpoint_driver.bin"), "wb") as f:
+                    f.write(b"PIGSDRV1" + np.uint64(v.size).tobytes() + v.tobytes())
+            else:
+                raw = open(self._p("checkpoint_driver.bin"), "rb").read()
+                if raw[:8] != b"PIGSDRV1" or int(np.frombuffer(raw[8:16], "<u8")[0]) != n:
+                    raise ValueError("checkpoint_driver.bin does not belong to this configuration")
+                v = np.frombuffer(raw[16:16 + 8 * n], "<f8")
+                iblock0, idiag_aux, obdm_bl, diag_bl = int(v[0]), int(v[1]), int(v[2]), int(v[3])
+                o = 4
+                for a in arrs:
+                    a[...] = v[o:o + a.size].reshape(a.shape)
+                    o += a.size
+
+        if getattr(self, "full_resume", False):
+            driver_state(False)
+        mode = "a" if getattr(self, "full_resume", False) else "w"
+        fe = open(self._p("e_vpi.out"), mode)
+        fet = open(self._p("et_vpi.out"), mode)
         self.blocks = []
-        for iblock in range(1, Nblock + 1):
+        every = int(c.get("checkpoint_every", 1))
+        for iblock in range(iblock0 + 1, Nblock + 1):
             t0 = time.perf_counter()
             be.run_block(Nstep)
             b, gr, Sk, nr = be.get_block()
@@ -289,22 +399,16 @@ class VpiDriver:
                 idiag_aux = 0
                 nrho[:] = 0.0
             self.checkpoint()
+            if hasattr(be, "save_checkpoint") and every > 0 and (iblock % every == 0 or iblock == Nblock):
+                be.save_checkpoint(self._p("checkpoint_chains.bin"))
+                iblock0 = iblock
+                driver_state(True)
+                fe.flush()
+                fet.flush()
             dt = time.perf_counter() - t0
             self.blocks.append(dict(b, means=m, time=dt))
-            pct = lambda a, t: 100.0 * a / t if t else float("nan")
-            self.say(" -----------------------------------------------------------")
-            self.say(f" BLOCK NUMBER : {iblock}")
-            for lab, i in (("<E> ", 0), ("<Ec>", 1), ("<Ep>", 2), ("<Et>", 3), ("<Kt>", 4), ("<Vt>", 5)):
-                self.say(f"   > {lab} ={fortran_g(m[i] / Np, 16, 8, 2)} +/-{fortran_g(bvar[i] / Np, 16, 8, 2)}")
-            self.say(f" > CM movements      = {pct(b['acc_cm'], b['try_cm']):7.2f} %")
-            self.say(f" > Staging movements = {pct(b['acc_bd'], b['try_stag']):7.2f} %")
-            self.say(f" > Head movements    = {pct(b['acc_head'], b['try_stag']):7.2f} %")
-            self.say(f" > Tail movements    = {pct(b['acc_tail'], b['try_stag']):7.2f} %")
-            self.say(f" > Diagonal conf.    = {pct(nd, Nstep * self.n_chains):7.2f} %")
-            self.say(f" > Open acc          = {pct(b['acc_open'], b['try_open']):7.2f} %")
-            self.say(f" > Close acc         = {pct(b['acc_close'], b['try_close']):7.2f} %")
-            self.say(f" > Swap acc          = {pct(b['acc_swap'], b['try_swap']):7.2f} %")
-            self.say(f" # Time per block    = {dt:7.2f} seconds   ({sum(b['bead_updates']) / dt:.4g} bead-updates/s)")
+            for ln in block_report_lines(iblock, m, bvar, b, Np, Nstep, self.n_chains, dt):      # vpi.f90:552-586
+                self.say(ln)
         fe.close()
         fet.close()
         # fort.99: permutation histogram (vpi.f90:590-592), summed over chains
@@ -319,10 +423,8 @@ class VpiDriver:
         if diag_bl:
             A, A2 = Av / diag_bl, Av2 / diag_bl
             V = [var(diag_bl, A[i], A2[i]) for i in range(6)]
-            self.say(" ==============================================================")
-            self.say(" FINAL RESULTS:")
-            for lab, i in (("<E> ", 0), ("<Ec>", 1), ("<Ep>", 2), ("<Et>", 3), ("<Kt>", 4), ("<Vt>", 5)):
-                self.say(f"   > {lab} ={fortran_g(A[i] / Np, 16, 8, 2)} +/-{fortran_g(V[i] / Np, 16, 8, 2)}")
+            for ln in final_lines(A, V, Np):                                   # vpi.f90:620-634
+                self.say(ln)
             res = dict(E=A[0] / Np, K=A[1] / Np, V=A[2] / Np, Et=A[3] / Np, Kt=A[4] / Np, Vt=A[5] / Np,
                        errE=V[0] / Np, errEt=V[3] / Np)
         if not trap and diag_bl:
@@ -369,6 +471,7 @@ def main(argv=None):
     ap.add_argument("--chains", type=int, default=None)
     ap.add_argument("--rng", default=None, choices=["philox", "mt"])
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--gpus", type=int, default=None, help="shard the chains over this many GPUs (inside the C ABI)")
     ap.add_argument("--potential", default="hfdb", choices=["hfdb", "hfdhe2", "zero"])
     a = ap.parse_args(argv)
     cfg = read_vpi_in(sys.stdin.read())
@@ -379,7 +482,10 @@ def main(argv=None):
     n = a.chains or int(cu.get("n_chains", 1))
     rng = a.rng or str(cu.get("rng", "mt" if n == 1 else "philox"))
     sim = PigsCuda(cfg, n_chains=n, rng=rng, device=a.device, threads_per_chain=int(cu.get("threads_per_chain", 0)),
-                   table_mode=int(cu.get("table_mode", -1)))
+                   table_mode=int(cu.get("table_mode", -1)), schedule=int(cu.get("schedule", -1)),
+                   gpus=a.gpus or int(cu.get("gpus", 1)))
+    if "checkpoint_every" in cu:
+        cfg["checkpoint_every"] = int(cu["checkpoint_every"])
     VpiDriver(cfg, sim, workdir=a.workdir, potential=a.potential).run()
 
 

@@ -108,6 +108,8 @@ def load_library() -> C.CDLL:
         "pigs_stream": (C.c_int, [H, C.POINTER(C.c_void_p)]),
         "pigs_launch_count": (C.c_int, [H, C.POINTER(C.c_int64)]),
         "pigs_launch_plan": (C.c_int, [H, ip, ip, ip, ip, ip]),
+        "pigs_save_checkpoint": (C.c_int, [H, C.c_char_p]),
+        "pigs_load_checkpoint": (C.c_int, [H, C.c_char_p]),
         "pigs_move": (C.c_int, [H, C.c_int, C.c_int, C.c_int, i32p, i32p]),
         "pigs_update_action": (C.c_int, [H, C.c_int, dp, i32p, i32p, dp, dp, dp]),
         "pigs_local_energy": (C.c_int, [H, C.c_int, dp, dp, dp, dp]),
@@ -484,6 +486,13 @@ class PigsCuda:
         d["bead_updates"] = np.array([list(o.bead_updates) for o in out])
         d["n_open_chains"] = np.array([o.n_open_chains for o in out])
         return d, gr, Sk[:, :self.Nk], nr
+
+    def save_checkpoint(self, path):
+        """every chain's complete device state (paths, worm/permutation state, RNG) in one binary file"""
+        self._ck(self.L.pigs_save_checkpoint(self.h, str(path).encode()))
+
+    def load_checkpoint(self, path):
+        self._ck(self.L.pigs_load_checkpoint(self.h, str(path).encode()))
 
     def launch_plan(self):
         v = [C.c_int() for _ in range(5)]

@@ -29,7 +29,7 @@ GROUPS = dict(
     wavefun=("Nmax", "wf_table", "v_table"),
     jastrow=("Rm",),
     extpot=("a_ho",),
-    cuda=("n_chains", "rng", "threads_per_chain", "table_mode", "gpus", "philox_seed", "action"),
+    cuda=("n_chains", "rng", "threads_per_chain", "table_mode", "gpus", "philox_seed", "action", "schedule", "checkpoint_every"),
 )
 REQUIRED = ("dim", "Np", "density", "dt", "Nb", "delta_cm", "CMFreq", "sampling", "Nstag", "Nblock", "Nstep", "Nbin",
             "Nk", "Rm")

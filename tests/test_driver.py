@@ -170,20 +170,20 @@ def test_vpi_cuda_matches_python_driver_byte_for_byte(tmp_path, cfgname):
     """the compiled program and the Python driver are the same program over the same C ABI: every file identical"""
     from pathintegralgroundstate_b200 import PigsCuda
     from tests.common import CS
-    cfg = dict(dict(CWX=CWX, C1=C1, CS=CS)[cfgname], Nblock=3, Nstep=8)
+    cfg = dict(dict(CWX=CWX, C1=C1, CS=CS)[cfgname], Nblock=3, Nstep=8, checkpoint_every=0)     # reference-style files only
     pot = "zero" if cfgname == "C1" else "hfdb"
     a, b = tmp_path / "cxx", tmp_path / "py"
-    out = _vpi(["--workdir", str(a), "--potential", pot], format_vpi_in(cfg, cuda=dict(n_chains=1, rng="mt")))
+    out = _vpi(["--workdir", str(a), "--potential", pot], format_vpi_in(cfg, cuda=dict(n_chains=1, rng="mt", checkpoint_every=0)))
     d = VpiDriver(cfg, PigsCuda(cfg, n_chains=1, rng="mt", seed=cfg["seed"]), workdir=str(b), potential=pot, quiet=True)
     d.run()
     files = ["e_vpi.out", "et_vpi.out", "gr_vpi.out", "sk_vpi.out", "nr_vpi.out", "fort.99", "checkpoint.dat", "rand_state",
              "jastrow.out", "potential.out"]
     _compare_run_dirs(a, b, files)
-    strip = lambda lines: [ln for ln in lines if not ln.startswith(" # Time per block")]
+    strip = lambda lines: [ln for ln in lines if not ln.startswith((" # Time per block", " # GPU throughput"))]
     assert strip(out.splitlines()) == strip(d.out)
     # resume from the files the compiled program wrote (vpi_mod.f90:162-185): both continue identically
     cfg2 = dict(cfg, resume=True, Nblock=2)
-    _vpi(["--workdir", str(a), "--potential", pot], format_vpi_in(cfg2, cuda=dict(n_chains=1, rng="mt")))
+    _vpi(["--workdir", str(a), "--potential", pot], format_vpi_in(cfg2, cuda=dict(n_chains=1, rng="mt", checkpoint_every=0)))
     VpiDriver(cfg2, PigsCuda(cfg2, n_chains=1, rng="mt", seed=cfg["seed"]), workdir=str(b), potential=pot, quiet=True).run()
     _compare_run_dirs(a, b, ["e_vpi.out", "et_vpi.out", "checkpoint.dat", "fort.99"])
 
@@ -192,7 +192,7 @@ def test_vpi_cuda_matches_python_driver_byte_for_byte(tmp_path, cfgname):
 def test_vpi_cuda_many_chains_philox(tmp_path):
     cfg = dict(CWX, Nblock=2, Nstep=6)
     out = _vpi(["--workdir", str(tmp_path)], format_vpi_in(cfg, cuda=dict(n_chains=64, rng="philox")))
-    assert "Markov chains (GPU) :    64" in out and "FINAL RESULTS" in out
+    assert "Markov chains (GPU) :    64" in out and "FINAL RESULTS" in out and " BLOCK NUMBER :           2" in out
     e = np.loadtxt(tmp_path / "e_vpi.out")
     assert e.shape == (2, 4) and np.all(np.isfinite(e))
 
@@ -223,6 +223,33 @@ def test_vpi_cuda_crystal_reads_config_ini(tmp_path):
                        text=True, cwd=ROOT, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     _compare_run_dirs(a, c, ["e_vpi.out", "et_vpi.out", "checkpoint.dat"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("first,second", [("cxx", "cxx"), ("py", "py"), ("cxx", "py")])
+def test_full_resume_continues_bit_for_bit(tmp_path, first, second):
+    """the extended checkpoint (checkpoint_chains.bin: every chain's path, worm/permutation state and RNG;
+    checkpoint_driver.bin: the accumulators the reference loses on restart): 2 blocks, stop, resume, 2 more blocks
+    == 4 uninterrupted blocks, byte for byte in every output file -- also across the two drivers"""
+    from pathintegralgroundstate_b200 import PigsCuda
+    n = 6
+    cuda = dict(n_chains=n, rng="philox")
+    files = ["e_vpi.out", "et_vpi.out", "gr_vpi.out", "sk_vpi.out", "nr_vpi.out", "fort.99", "checkpoint.dat", "checkpoint_chains.bin",
+             "checkpoint_driver.bin"]
+
+    def run(which, wd, cfg):
+        if which == "cxx":
+            _vpi(["--workdir", str(wd)], format_vpi_in(cfg, cuda=cuda))
+        else:
+            VpiDriver(cfg, PigsCuda(cfg, n_chains=n, rng="philox", seed=cfg["seed"]), workdir=str(wd), quiet=True).run()
+
+    whole, parts = tmp_path / "whole", tmp_path / "parts"
+    run(first, whole, dict(CWX, Nblock=4, Nstep=8))
+    run(first, parts, dict(CWX, Nblock=2, Nstep=8))
+    assert np.loadtxt(parts / "e_vpi.out").shape[0] <= 2
+    run(second, parts, dict(CWX, Nblock=4, Nstep=8, resume=True))
+    _compare_run_dirs(whole, parts, files)
+    assert np.loadtxt(whole / "e_vpi.out").ndim == 2
 
 
 NASTY_VPI_IN = """! leading comment with & and / characters

@@ -197,3 +197,38 @@ def test_inputs_the_reference_lacks(tmp_path):
     assert bl[0][0] == 1 and abs(bl[-1][1] - bl[0][1]) < 0.5 * bl[0][1]          # white noise: flat blocking curve
     jm, je = jackknife(x)
     assert jm == pytest.approx(x.mean()) and je == pytest.approx(e, rel=0.05)
+
+
+def test_cross_chain_statistics_layer():
+    """BlockSeries / ratio / permutation_cycles on a stand-in for the GPU handle (the layer itself is host code)"""
+    from pathintegralgroundstate_b200.statistics import BlockSeries, ratio, permutation_cycles, chain_means
+
+    class Fake:
+        n_chains, Np = 40, 6
+
+        def __init__(self):
+            self.rng = np.random.default_rng(4)
+
+        def get_block_chains(self, chain0=0, n=None):
+            n = self.n_chains - chain0 if n is None else n
+            nd = self.rng.integers(5, 15, n)
+            b = dict(sumE=-3.0 * nd + self.rng.normal(0, 0.3, n), sumK=nd * 1.0, sumV=nd * -4.0, sumEt=nd * -2.9, sumKt=nd * 1.1,
+                     sumVt=nd * -4.0, idiag_block=nd, ngr=nd)
+            return b, np.ones((n, 4)), np.zeros((n, 2, 3)), np.ones((n, 4, 1))
+
+        def get_perm(self, c):
+            return 1, np.zeros(self.Np, np.int32), np.array([3, 1, 0, 0, 0, 0] if c % 2 else [0] * 6, np.int32)
+
+    sim = Fake()
+    bs = BlockSeries()
+    for _ in range(6):
+        bs.add(sim)
+    assert bs.series("sumE").shape == (6, 40)
+    e, err = bs.energy_per_particle(Np=1)
+    assert abs(e + 3.0) < 5 * err and 0 < err < 0.02
+    r, rerr = ratio([1, 2, 3, 4], [2, 4, 6, 8])
+    assert r == 0.5 and rerr < 1e-12
+    hist, P, mean_len, contributing = permutation_cycles(sim)
+    assert hist.tolist() == [60, 20, 0, 0, 0, 0] and contributing == 20 and mean_len == pytest.approx(1.25) and P.sum() == pytest.approx(1.0)
+    cm = chain_means(sim, chains=[3, 5, 9])
+    assert cm["sumE"].shape == (3,) and np.all(np.isfinite(cm["sumE"]))
