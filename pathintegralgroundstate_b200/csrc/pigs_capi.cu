@@ -38,7 +38,7 @@ struct pigs_ctx {
     float last_ms = 0.f;
     long long launches = 0;
     // device buffers
-    double *d_logwf = nullptr, *d_vtab = nullptr, *d_path = nullptr, *d_xend = nullptr, *d_acc = nullptr, *d_vec = nullptr;
+    double *d_logwf = nullptr, *d_vtab = nullptr, *d_path = nullptr, *d_xend = nullptr, *d_acc = nullptr, *d_vec = nullptr, *d_pp = nullptr;
     double* d_stage = nullptr;      // AoS staging for state transfer
     int *d_istate = nullptr, *d_cyc = nullptr, *d_hist = nullptr, *d_iout = nullptr;
     unsigned* d_mt = nullptr;
@@ -275,7 +275,7 @@ static int init_single(pigs_ctx* h, const pigs_params* p) {
     ALLOC(h->d_path, nc * P.chain_stride); ALLOC(h->d_xend, nc * 6);
     ALLOC(h->d_istate, nc * IS_N); ALLOC(h->d_cyc, nc * P.Np); ALLOC(h->d_hist, nc * P.Np);
     ALLOC(h->d_mt, nc * 624); ALLOC(h->d_pctr, nc * PCS); ALLOC(h->d_acc, nc * P.nacc); ALLOC(h->d_cnt, nc * NCNT);
-    ALLOC(h->d_vec, h->nvec); ALLOC(h->d_iout, nc * 2);
+    ALLOC(h->d_vec, h->nvec); ALLOC(h->d_iout, nc * 2); ALLOC(h->d_pp, nc * P.Np);
 #undef ALLOC
     CK(cudaMemset(h->d_path, 0, sizeof(double) * nc * P.chain_stride));
     CK(cudaMemset(h->d_xend, 0, sizeof(double) * nc * 6));
@@ -288,7 +288,7 @@ static int init_single(pigs_ctx* h, const pigs_params* p) {
     CK(cudaMemset(h->d_logwf, 0, sizeof(double) * tab_len(p->Nmax)));
     CK(cudaMemset(h->d_vtab, 0, sizeof(double) * tab_len(p->Nmax)));
     P.logwf = h->d_logwf; P.vtab = h->d_vtab; P.path = h->d_path; P.xend = h->d_xend; P.istate = h->d_istate;
-    P.cyc = h->d_cyc; P.hist = h->d_hist; P.mt = h->d_mt; P.pctr = h->d_pctr; P.acc = h->d_acc; P.cnt = h->d_cnt;
+    P.cyc = h->d_cyc; P.hist = h->d_hist; P.mt = h->d_mt; P.pctr = h->d_pctr; P.acc = h->d_acc; P.cnt = h->d_cnt; P.pp = h->d_pp;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
     CK(cudaMalloc((void**)&h->d_flag, sizeof(int)));
@@ -381,7 +381,7 @@ extern "C" int pigs_destroy(pigs_handle h) {
     cudaFree(h->d_flag);
     cudaFree(h->d_logwf); cudaFree(h->d_vtab); cudaFree(h->d_path); cudaFree(h->d_xend); cudaFree(h->d_istate);
     cudaFree(h->d_cyc); cudaFree(h->d_hist); cudaFree(h->d_mt); cudaFree(h->d_pctr); cudaFree(h->d_acc);
-    cudaFree(h->d_cnt); cudaFree(h->d_vec); cudaFree(h->d_iout); cudaFree(h->d_stage);
+    cudaFree(h->d_cnt); cudaFree(h->d_vec); cudaFree(h->d_iout); cudaFree(h->d_stage); cudaFree(h->d_pp);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->st) cudaStreamDestroy(h->st);

@@ -18,10 +18,10 @@
 // memory, and every shared helper is a real (noinline) function so the 14 moves
 // are thin glue around one copy of the hot code.
 //
-// Data layout in HBM (per chain): path[ib][k][ip] -- structure-of-arrays per
-// time slice so that lane<->partner loads are unit-stride and coalesced
-// (the ABI layout Path(dim,Np,0:2Nb) is array-of-structures; the library
-// transposes on upload/download).  Unused components (dim<3) are zero.
+// Data layout in HBM (per chain): path[ib][ip/32][k][ip%32] -- a time slice is NpS/32 blocks of [3][32] doubles
+// (x, y, z of 32 consecutive particles side by side, 768 contiguous bytes), so lane<->partner loads are
+// unit-stride and one block is one DRAM burst (see pidx below).  The ABI layout Path(dim,Np,0:2Nb) is
+// array-of-structures; the library transposes on upload/download.  Unused components (dim<3) are zero.
 #pragma once
 
 #include <cstdint>
@@ -80,6 +80,7 @@ struct DevParams {
     int* hist;                // [chain][Np]  Perm_histogram
     unsigned* mt;             // [chain][624]
     unsigned long long* pctr; // [chain][PCS] Philox counters
+    double* pp;               // [chain][Np]  Swap's tower-sampling weights (vpi_mod.f90:2334-2345): rare, so not in smem
     double* acc;              // [chain][nacc]
     long long* cnt;           // [chain][NCNT]
     size_t chain_stride;      // doubles per chain in path
@@ -132,6 +133,7 @@ struct GS {
     int* cyc;
     int* hist;
     unsigned* mt;
+    double* pp;          // Swap's Pp(Np) scratch, global memory
     const double* tabV;  // table bases: shared-memory copies when staged, else global
     const double* tabW;
     double bc[8];        // broadcast slots
@@ -146,7 +148,7 @@ struct GS {
     // windows of the current pass of the window-ordered sweep (win_sweep): head / tail lengths, middle starts
     int wLh, wLt, wM0, wM1, wnM;
     MovePark pk;
-    // followed by: seg_old[3S] seg_new[3S] part[np*8] pp[Np]
+    // followed by: seg_old[3S] seg_new[3S] part[np*8]
 };
 // ------------------------------------------------------------------ group
 struct Grp {
@@ -178,12 +180,13 @@ __device__ __forceinline__ void tsync() {
 __device__ __forceinline__ bool gfirst(const GS* gs) { return (threadIdx.x & (gsize_of(gs) - 1)) == 0; }
 __host__ __device__ inline int part_slots(int nwarps) { return nwarps < 4 ? 4 : nwarps; }
 __host__ __device__ inline size_t grp_smem_bytes(int S, int Np, int nwarps) {
-    return sizeof(GS) + sizeof(double) * ((size_t)6 * S + (size_t)part_slots(nwarps) * 8 + (size_t)Np);
+    (void)Np;
+    return sizeof(GS) + sizeof(double) * ((size_t)6 * S + (size_t)part_slots(nwarps) * 8);
 }
 __device__ __forceinline__ double* seg_old(GS* gs) { return reinterpret_cast<double*>(gs + 1); }
 __device__ __forceinline__ double* seg_new(GS* gs) { return seg_old(gs) + 3 * cP.S; }
 __device__ __forceinline__ double* part_of(GS* gs) { return seg_old(gs) + 6 * cP.S; }
-__device__ __forceinline__ double* pp_of(GS* gs) { return part_of(gs) + part_slots(cA.threads_per_chain >> 5) * 8; }
+__device__ __forceinline__ double* pp_of(GS* gs) { return gs->pp; }
 __device__ __forceinline__ double& so(GS* gs, int k, int ib) { return seg_old(gs)[k * cP.S + ib]; }
 __device__ __forceinline__ double& sn(GS* gs, int k, int ib) { return seg_new(gs)[k * cP.S + ib]; }
 // A time slice is stored as NpS/32 blocks of [3][32] doubles: x, y, z of 32
@@ -501,8 +504,7 @@ __device__ __forceinline__ void rng_gauss_fill(GS* gs, RngS* pst, int dim, int b
 // KIND: 0 interior even slice   -> pot
 //       1 odd slice (Chin term) -> pot, Fnew(3), Fold(3)
 //       2 end slice (Jastrow)   -> pot, psi
-// Each class has its own loop with only its accumulators live (the kernel runs
-// at 64 registers per thread; ncu showed spills in a shared 8-accumulator loop).
+// (One loop serves the three classes, see pair_loop; the kernel runs at 128 registers per thread.)
 //
 // Branch-free: a partner outside the cutoff (or the moved particle itself) is
 // evaluated at r = rcut with weight 0, so the new and old positions form
@@ -567,14 +569,7 @@ __device__ __forceinline__ Partner load_partner(const double* Rx, int j) {
     return p;
 }
 
-// ONE partner loop for the three slice classes (kind is warp-uniform, so the
-// class-specific parts are skipped by uniform branches): the hot code of all
-// warps of a scheduler is then the same ~2.5 KB and stays in the L0 instruction
-// cache (three specialised loops were 6.6 KB; ncu showed 1.3 no_instruction
-// stall cycles per issue).
-// acc: pot, psi, fn[3], fo[3].  `first` = coordinates of partner j0, preloaded
-// by the caller (during the previous bead's reduction / the proposal).
-// both positions of the displaced bead against ONE partner
+// both positions of the displaced bead against ONE partner (round-1 form; pair_body2 below is the production one)
 template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
 __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& cur, const double (&xo)[3],
                                           const double (&xn)[3], double& pot, double& psi, double (&fn)[3], double (&fo)[3]) {
@@ -716,7 +711,7 @@ __device__ __forceinline__ Pos2 pos_geom(double d0, double d1, double d2) {
         else { g.ir = 0.0; r = (PIGS_LOOPV & 16) ? sqrt_q(r2) : sqrt_pos(r2); }
         const double MAGIC = 6755399441055744.0;
         const double m = __fma_rd(r, cP.inv_dr, MAGIC);
-        g.k.i0 = in ? __double2loint(m) : cP.Nmax + 3;
+        g.k.i0 = in ? max(__double2loint(m), 1) : cP.Nmax + 3;     // i0 >= 1: the centred difference reads F(i0-1) (r < dr never survives a Metropolis test)
         g.k.t = fma(r, cP.inv_dr, -(m - MAGIC));
         return g;
     }
@@ -835,7 +830,10 @@ __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
 template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
 __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, int j0, int jstride, bool add_self,
                                             const double (&xo)[3], const double (&xn)[3], int lane, double* part,
-                                            const Partner& first) {
+                                            const Partner& first, double* lin = nullptr) {
+    // lin != nullptr (whole partner range in this warp): the part of DeltaS that is LINEAR in the per-lane sums -- the
+    // potential and Jastrow terms -- is handed back unreduced in *lin (the caller reduces once per evaluation instead
+    // of once per bead); only the Chin force term, quadratic in the reduced force, is reduced here and returned.
     int kind = bead_kind(ib);
     asm volatile("" : "+r"(kind));      // opaque: keeps the class in a register instead of re-deriving it from ib every iteration
     double pot = 0.0, psi = 0.0, fn[3] = {0.0, 0.0, 0.0}, fo[3] = {0.0, 0.0, 0.0};
@@ -852,6 +850,18 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
     }
     if (PIGS_LOOPV != 0 && !TRAP && !VPAIR) pair_loop2<VSM, WSM>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
     else pair_loop<TRAP, VSM, WSM, VPAIR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
+    if (lin) {
+        if (kind == 0) { *lin = cP.wS[ib & 1] * pot; return 0.0; }
+        if (kind == 2) { *lin = fma(cP.wS[2], pot, -psi); return 0.0; }
+        *lin = cP.wS[1] * pot;
+        const double a6[8] = {0.0, 0.0, fn[0], fn[1], fn[2], fo[0], fo[1], fo[2]};
+        const double v6 = warp_sum8(a6, lane);
+        const int q6 = lane >> 2;
+        const double c6 = cP.cF;
+        double t6 = (q6 < 2) ? 0.0 : ((q6 < 5) ? c6 * v6 * v6 : -c6 * v6 * v6);
+        t6 += shx(t6, 4); t6 += shx(t6, 8); t6 += shx(t6, 16);
+        return t6;
+    }
     if (kind == 0) {
         double v = warp_sum(pot);
         if (!part) return cP.wS[ib & 1] * v;

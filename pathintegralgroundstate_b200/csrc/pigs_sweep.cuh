@@ -89,7 +89,7 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         const double* Rx = slice(gs, b0);                                  // walks the evaluated slices
         const long long sstride = (long long)bstride * 3 * cP.NpS, pfoff = (long long)cA.pfdist * sstride;
         if (have) first = load_partner(Rx, lane);
-        double Sw = 0.0;
+        double Sw = 0.0, Slin = 0.0;       // Slin: per-lane sum of the terms linear in the pair sums, reduced once below
         for (int m = 0; m < nb; ++m, Rx += sstride) {
             const int ib = b0 + m * bstride;
             double xo[3], xn[3];
@@ -98,12 +98,14 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
             const Partner cur = first;
             if (m + 1 < nb && have) first = load_partner(Rx + sstride, lane);
             if (roll && lane == 0 && m + cA.pfdist < nb) prefetch_slice_L2(Rx + pfoff);
+            double lin;
             const double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM, PIGS_VPAIR>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn,
-                                                                                 lane, nullptr, cur);
+                                                                                 lane, nullptr, cur, &lin);
             const double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
             Sw += w * t;
+            Slin += w * lin;
         }
-        return Sw;
+        return Sw + warp_sum(Slin);
     }
 #endif
     int split = 1;
@@ -1217,6 +1219,7 @@ PIGS_T __device__ __forceinline__ void sweep_body() {
             b->cyc = cP.cyc + (size_t)c * cP.Np;
             b->hist = cP.hist + (size_t)c * cP.Np;
             b->mt = cP.mt + (size_t)c * 624;
+            b->pp = cP.pp + (size_t)c * cP.Np;
             b->tabV = tV; b->tabW = tW;
             b->chain = c + cP.chain_offset;
             b->gsize = tid == 0 ? T : 32; b->gshift = tid == 0 ? cA.tshift : 5; b->gbar = g;

@@ -72,10 +72,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise PigsError(f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+    path = os.environ.get("PIGS_CUDA_LIB", LIB_PATH)      # tuning builds (e.g. another launch bound) for A/B runs
+    if not os.path.exists(path):
+        raise PigsError(f"{path} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
                         "(there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     dp, i32p, u32p = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
     H = C.c_void_p
     ip = C.POINTER(C.c_int)

@@ -2,12 +2,16 @@
 mkdir -p gpurun_out
 run() { python bench.py --steps 4 --warmup 3 --no-cpu-baseline "$@" 2>>gpurun_out/r2_quick.err | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('$*', '->', round(d['value']/1e6,1), 'M/s  e2e', round(d['e2e']['value']/1e6,1), ' frac', round(d['roofline']['frac'],4), d['config'].get('schedule'), d['config'].get('chains_per_gpu'))"; }
+d=json.loads(sys.stdin.read()); print('$PIGS_CUDA_LIB $PIGS_PREFETCH $*', '->', round(d['value']/1e6,1), 'M/s  e2e', round(d['e2e']['value']/1e6,1), ' frac', round(d['roofline']['frac'],4), d['config'].get('schedule'), d['config'].get('chains_per_gpu'))"; }
 {
+run --workload C3
 run --workload C2 --mc-steps 8
 run --workload C5 --chains 4096 --mc-steps 8
 run --workload C5 --chains 512 --schedule 1 --mc-steps 20
-run --workload C3
+PIGS_PREFETCH=0 run --workload C3
+PIGS_CUDA_LIB=$PWD/pathintegralgroundstate_b200/libpigs_cuda_640.so run --workload C3 --chains 2960
+PIGS_CUDA_LIB=$PWD/pathintegralgroundstate_b200/libpigs_cuda_768.so run --workload C3 --chains 3552
+PIGS_CUDA_LIB=$PWD/pathintegralgroundstate_b200/libpigs_cuda_640.so run --workload C2 --chains 2960 --mc-steps 8
 } > gpurun_out/r2_quick.log 2>&1
 cat gpurun_out/r2_quick.log; tail -3 gpurun_out/r2_quick.err
-python -m pytest tests/test_driver.py -m gpu -x -q 2>&1 | tail -5
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
