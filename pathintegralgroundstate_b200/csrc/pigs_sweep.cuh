@@ -1189,12 +1189,46 @@ PIGS_T __device__ __forceinline__ void sweep_body() {
         for (int i = threadIdx.x; i < ntab - 1; i += blockDim.x) { sp[2 * i] = cP.vtab[i]; sp[2 * i + 1] = cP.vtab[i + 1]; }
         tV = cP.vtab; sp += 2 * (ntab - 1);
     } else if (VT::VSM) {
-        for (int i = threadIdx.x; i < ntab; i += blockDim.x) sp[i] = cP.vtab[i];
         tV = sp; sp += ntab;
     }
-    if (VT::WSM) {
-        for (int i = threadIdx.x; i < ntab; i += blockDim.x) sp[i] = cP.logwf[i];
-        tW = sp; sp += ntab;
+    if (VT::WSM) { tW = sp; sp += ntab; }
+    if (!VT::VPAIR && (VT::VSM || VT::WSM)) {
+        // Table staging by the TMA engine: 1-D bulk copies global -> shared (cp.async.bulk, UBLKCP in SASS) issued by
+        // one thread and completed on an mbarrier -- 160 KB per CTA in a few microseconds instead of 40 rounds of
+        // LDG + STS by every thread (ncu, round 2: the copy loop held 3 % of the samples of a 2-step launch).
+        __shared__ __align__(8) unsigned long long stage_bar;
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+        const unsigned nbytes = (unsigned)ntab * 8u;
+        const bool bulk = (nbytes & 15u) == 0;               // bulk copies move multiples of 16 bytes
+        unsigned done = 0;
+        if (bulk) {
+            if (threadIdx.x == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned total = nbytes * ((VT::VSM ? 1u : 0u) + (VT::WSM ? 1u : 0u));
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+                for (int which = 0; which < 2; ++which) {
+                    if (which == 0 ? !VT::VSM : !VT::WSM) continue;
+                    const char* src = reinterpret_cast<const char*>(which == 0 ? cP.vtab : cP.logwf);
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(which == 0 ? tV : tW);
+                    for (unsigned off = 0; off < nbytes; off += 32768u) {
+                        const unsigned len = nbytes - off < 32768u ? nbytes - off : 32768u;
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(dst + off), "l"(src + off), "r"(len), "r"(bar) : "memory");
+                    }
+                }
+            }
+            for (int spin = 0; !done && spin < (1 << 22); ++spin)      // bounded: a copy that never lands must not hang the GPU
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(bar) : "memory");
+        }
+        if (!__syncthreads_and((int)done)) {                 // odd table length (or a copy that did not complete): plain loop
+            if (VT::VSM) for (int i = threadIdx.x; i < ntab; i += blockDim.x) const_cast<double*>(tV)[i] = cP.vtab[i];
+            if (VT::WSM) for (int i = threadIdx.x; i < ntab; i += blockDim.x) const_cast<double*>(tW)[i] = cP.logwf[i];
+        }
     }
     __syncthreads();           // last CTA-wide barrier: groups run independently from here on
 

