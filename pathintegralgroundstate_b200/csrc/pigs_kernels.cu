@@ -15,7 +15,12 @@ namespace pigs {
 // PIGS_MAXT = 512 gives the move engine 128 registers per thread: measured on
 // B200, 16 spill-free warps per SM beat 24 (80 regs) and 32 (64 regs, spilling
 // in the partner loop) for both the N=64 and the N=256 workloads.
+#ifdef PIGS_MAXNREG
+// tuning builds: an explicit register budget (the launcher still starts at most PIGS_MAXT threads per CTA)
+__global__ void __maxnreg__(PIGS_MAXNREG) PIGS_KNAME() { sweep_body<(PIGS_INST_MT != 0), PIGS_INST_VAR>(); }
+#else
 __global__ void __launch_bounds__(PIGS_MAXT, 1) PIGS_KNAME() { sweep_body<(PIGS_INST_MT != 0), PIGS_INST_VAR>(); }
+#endif
 
 cudaError_t PIGS_LNAME(int what, const DevParams* P, const SweepArgs* A, int grid, int block, size_t smem,
                        cudaStream_t st, int* out) {
