@@ -649,6 +649,9 @@ PIGS_PRAGMA_UNROLL
 //   4   wrap count of the minimum image from a compare on the high word of d: -12 FP64 slots, +10 ALU   635 / 678 (slower)
 //   8   table reads through explicit ld.shared with a 32-bit base: no change
 //   64  L1 prefetch two blocks ahead + L1-allocating loads: 593 / 639 (slower);  128 L1-allocating loads only: 648 / 706
+//   256 two partner blocks per iteration (four dependency chains per warp), partner registers carried from bead to bead:
+//       isolated loop 515 -> 663 (HBM, no prefetch) / 679 -> 696 (L2) / N=64 1564 -> 1758, but INSIDE the sweep kernel, at
+//       its 128-register cap, ptxas serialises the four chains: C3 457 -> 425 M, C2 894 -> 755 M.  Off.
 // Variants 1 and 32 give results bit-identical to variant 0.
 #ifndef PIGS_LOOPV
 #define PIGS_LOOPV 33
@@ -778,10 +781,16 @@ __device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW,
         if (kind == 2) psi += lk2_val<WSM, 1, VSM>(gn.k, sbW) - lk2_val<WSM, 1, VSM>(go.k, sbW);
     }
 }
+// partner registers carried from bead to bead by the two-block loop (PIGS_LOOPV & 256): blocks j0 and j0 + jstride of
+// the slice about to be evaluated, and the slice after it (nullptr: none)
+struct Carry {
+    Partner a, b;
+    const double* next;
+};
 template <bool VSM, bool WSM>
 __device__ __forceinline__ void pair_loop2(int kind, const double* Rx, int ip0, int j0, int jstride, const double (&xo)[3],
                                            const double (&xn)[3], Partner cur, double& pot, double& psi, double (&fn)[3],
-                                           double (&fo)[3]) {
+                                           double (&fo)[3], Carry* cy = nullptr) {
     const double* p = Rx + pidx(j0);
     const int pstep = 3 * jstride;
     const int self_left = cP.Np - ip0;
@@ -790,6 +799,36 @@ __device__ __forceinline__ void pair_loop2(int kind, const double* Rx, int ip0, 
         extern __shared__ __align__(16) double pigs_smem_base[];
         sbV = (unsigned)__cvta_generic_to_shared(pigs_smem_base);
         sbW = sbV + (unsigned)cP.tabW_off;
+    }
+    if ((PIGS_LOOPV & 256) && cy) {
+        // Two partner blocks per iteration: four independent dependency chains per warp instead of two.  The partner
+        // registers are a stream that runs across beads: after their last use in a bead they are reloaded with the
+        // first two blocks of the NEXT evaluated slice (cy->next), so no load is ever exposed at a loop entry.
+        // Same accumulators, same order of additions as the one-block loop: bit-identical results.
+        Partner a = cy->a, b = cy->b;
+        const double* pn = cy->next ? cy->next + pidx(j0) : nullptr;
+        const int left0 = cP.Np - j0;
+        for (int left = left0; left > 0; left -= 2 * jstride) {
+            if (left <= jstride) b.x = 1e150;                   // no second block: zero tail
+            if (left == self_left) a.x = 1e150;
+            if (left - jstride == self_left) b.x = 1e150;
+            const double an0 = xn[0] - a.x, an1 = xn[1] - a.y, an2 = xn[2] - a.z;
+            const double aq0 = xo[0] - a.x, aq1 = xo[1] - a.y, aq2 = xo[2] - a.z;
+            const double bn0 = xn[0] - b.x, bn1 = xn[1] - b.y, bn2 = xn[2] - b.z;
+            const double bq0 = xo[0] - b.x, bq1 = xo[1] - b.y, bq2 = xo[2] - b.z;
+            p += 2 * pstep;
+            if (left > 2 * jstride) {
+                a.x = ldpath(p); a.y = ldpath(p + PY); a.z = ldpath(p + PZ);
+                if (left > 3 * jstride) { b.x = ldpath(p + pstep); b.y = ldpath(p + pstep + PY); b.z = ldpath(p + pstep + PZ); }
+            } else if (pn) {
+                a.x = ldpath(pn); a.y = ldpath(pn + PY); a.z = ldpath(pn + PZ);
+                if (left0 > jstride) { b.x = ldpath(pn + pstep); b.y = ldpath(pn + pstep + PY); b.z = ldpath(pn + pstep + PZ); }
+            }
+            pair_body2<VSM, WSM>(kind, sbV, sbW, an0, an1, an2, aq0, aq1, aq2, pot, psi, fn, fo);
+            pair_body2<VSM, WSM>(kind, sbV, sbW, bn0, bn1, bn2, bq0, bq1, bq2, pot, psi, fn, fo);
+        }
+        cy->a = a; cy->b = b;
+        return;
     }
 PIGS_PRAGMA_UNROLL
     for (int left = cP.Np - j0; left > 0; left -= jstride) {
@@ -830,7 +869,7 @@ __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
 template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
 __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, int j0, int jstride, bool add_self,
                                             const double (&xo)[3], const double (&xn)[3], int lane, double* part,
-                                            const Partner& first, double* lin = nullptr) {
+                                            const Partner& first, double* lin = nullptr, Carry* cy = nullptr) {
     // lin != nullptr (whole partner range in this warp): the part of DeltaS that is LINEAR in the per-lane sums -- the
     // potential and Jastrow terms -- is handed back unreduced in *lin (the caller reduces once per evaluation instead
     // of once per bead); only the Chin force term, quadratic in the reduced force, is reduced here and returned.
@@ -848,7 +887,7 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
             }
         }
     }
-    if (PIGS_LOOPV != 0 && !TRAP && !VPAIR) pair_loop2<VSM, WSM>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
+    if (PIGS_LOOPV != 0 && !TRAP && !VPAIR) pair_loop2<VSM, WSM>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo, cy);
     else pair_loop<TRAP, VSM, WSM, VPAIR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
     if (lin) {
         if (kind == 0) { *lin = cP.wS[ib & 1] * pot; return 0.0; }

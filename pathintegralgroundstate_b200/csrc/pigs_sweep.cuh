@@ -84,11 +84,15 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         // decomposition, no partial-sum exchange
         const int lane = G.lane;
         const bool have = lane < cP.Np;
+        constexpr bool TWO = (PIGS_LOOPV & 256) && !PIGS_TRAP && !PIGS_VPAIR;      // two-block partner loop, see pair_loop2
         Partner first;
+        Carry cy;
         first.x = first.y = first.z = 0.0;
+        cy.a = first; cy.b = first;
         const double* Rx = slice(gs, b0);                                  // walks the evaluated slices
         const long long sstride = (long long)bstride * 3 * cP.NpS, pfoff = (long long)cA.pfdist * sstride;
         if (have) first = load_partner(Rx, lane);
+        if (TWO) { cy.a = first; if (lane + 32 < cP.Np) cy.b = load_partner(Rx, lane + 32); }
         double Sw = 0.0, Slin = 0.0;       // Slin: per-lane sum of the terms linear in the pair sums, reduced once below
         for (int m = 0; m < nb; ++m, Rx += sstride) {
             const int ib = b0 + m * bstride;
@@ -96,11 +100,12 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
 #pragma unroll
             for (int k = 0; k < 3; ++k) { xo[k] = so(gs, k, ib); xn[k] = sn(gs, k, ib); }
             const Partner cur = first;
-            if (m + 1 < nb && have) first = load_partner(Rx + sstride, lane);
+            if (TWO) cy.next = (m + 1 < nb) ? Rx + sstride : nullptr;
+            else if (m + 1 < nb && have) first = load_partner(Rx + sstride, lane);
             if (roll && lane == 0 && m + cA.pfdist < nb) prefetch_slice_L2(Rx + pfoff);
             double lin;
             const double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM, PIGS_VPAIR>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn,
-                                                                                 lane, nullptr, cur, &lin);
+                                                                                 lane, nullptr, cur, &lin, TWO ? &cy : nullptr);
             const double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
             Sw += w * t;
             Slin += w * lin;

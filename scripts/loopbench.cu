@@ -8,8 +8,11 @@
 #include <cstring>
 using namespace pigs;
 
+#ifndef LB_THREADS
+#define LB_THREADS 512
+#endif
 template <int KINDSEL>
-__global__ void __launch_bounds__(512, 1) k_loop(const double* slices, int nslices, int iters, double* out) {
+__global__ void __launch_bounds__(LB_THREADS, 1) k_loop(const double* slices, int nslices, int iters, double* out) {
     extern __shared__ __align__(16) double pigs_smem_base[];
     const int ntab = tab_len(cP.Nmax);
     for (int i = threadIdx.x; i < ntab; i += blockDim.x) { pigs_smem_base[i] = cP.vtab[i]; pigs_smem_base[ntab + i] = cP.logwf[i]; }
@@ -19,6 +22,7 @@ __global__ void __launch_bounds__(512, 1) k_loop(const double* slices, int nslic
     double acc = 0.0;
     const size_t ss = (size_t)3 * cP.NpS;
     Partner first; first.x = first.y = first.z = 0.0;
+    Carry cy; cy.a = first; cy.b = first; cy.next = nullptr;
     for (int it = 0; it < iters; ++it) {
         h = h * 1664525u + 1013904223u;
         int s = (h >> 8) % nslices;
@@ -38,8 +42,14 @@ __global__ void __launch_bounds__(512, 1) k_loop(const double* slices, int nslic
         int ib = KINDSEL == 0 ? 2 : (KINDSEL == 1 ? 3 : (KINDSEL == 2 ? 0 : 1 + (int)((h >> 20) % 29)));
         double xo[3] = {Rx[pidx(ip0)], Rx[pidx(ip0) + PY], Rx[pidx(ip0) + PZ]};
         double xn[3] = {xo[0] + 0.05, xo[1] - 0.03, xo[2] + 0.02};
+#if PIGS_LOOPV & 256
+        if (it == 0) { cy.a = load_partner(Rx, lane); if (lane + 32 < cP.Np) cy.b = load_partner(Rx, lane + 32); }
+        cy.next = slices + (size_t)(((h * 1664525u + 1013904223u) >> 8) % nslices) * ss;      // the slice of the next iteration
+        acc += bead_eval<false, true, true, false>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn, lane, nullptr, first, nullptr, &cy);
+#else
         if (lane < cP.Np) first = load_partner(Rx, lane);
         acc += bead_eval<false, true, true, false>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn, lane, nullptr, first);
+#endif
     }
     if (lane == 0) out[warp] = acc;
 }
