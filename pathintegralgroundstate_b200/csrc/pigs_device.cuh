@@ -652,6 +652,10 @@ PIGS_PRAGMA_UNROLL
 //   256 two partner blocks per iteration (four dependency chains per warp), partner registers carried from bead to bead:
 //       isolated loop 515 -> 663 (HBM, no prefetch) / 679 -> 696 (L2) / N=64 1564 -> 1758, but INSIDE the sweep kernel, at
 //       its 128-register cap, ptxas serialises the four chains: C3 457 -> 425 M, C2 894 -> 755 M.  Off.
+//   512 in-range compaction (pair_loop3: cheap scan of every partner, the 52 % inside the cutoff sphere go through a
+//       per-warp shared-memory ring and get the square root / table / force part in dense batches of 32): FP64 slots
+//       per bead-update -25 %, yet 716 -> 559 (L2), 528 -> 466 (HBM), N=64 1633 -> 1306: scan -> ballot -> ring ->
+//       dense is one serial chain per block, and the loop is latency-bound, not slot-bound.  Off.
 // Variants 1 and 32 give results bit-identical to variant 0.
 #ifndef PIGS_LOOPV
 #define PIGS_LOOPV 33
@@ -696,10 +700,12 @@ __device__ __forceinline__ void rsqrt_sqrt_q(double x, double& ir, double& r) {
     ir = fma(0.5 * y, e, y);
     r = fma(0.5 * r0, e, r0);
 }
-template <bool NEED_IR>
+template <bool NEED_IR, bool WRAPPED = false>
 __device__ __forceinline__ Pos2 pos_geom(double d0, double d1, double d2) {
     Pos2 g;
-    if (PIGS_LOOPV & 4) {
+    if (WRAPPED) {                   // the components are minimum-image components already
+        g.d0 = d0; g.d1 = d1; g.d2 = d2;
+    } else if (PIGS_LOOPV & 4) {
         g.d0 = mimg_hi(d0, cP.L[0], cP.LhF[0]); g.d1 = mimg_hi(d1, cP.L[1], cP.LhF[1]); g.d2 = mimg_hi(d2, cP.L[2], cP.LhF[2]);
     } else {
         g.d0 = mimg_fast(d0, cP.L[0], cP.invL[0]); g.d1 = mimg_fast(d1, cP.L[1], cP.invL[1]); g.d2 = mimg_fast(d2, cP.L[2], cP.invL[2]);
@@ -754,12 +760,12 @@ __device__ __forceinline__ void lk2_val_d1(const Lk& k, unsigned sb, double& v, 
     lk_val_d1<SM, WHICH, VF>(k, v, d1);
 }
 // both positions of the displaced bead against ONE partner; dn/dq = x_new - r_j, x_old - r_j before the minimum image
-template <bool VSM, bool WSM>
+template <bool VSM, bool WSM, bool WRAPPED = false>
 __device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW, double dn0, double dn1, double dn2, double dq0,
                                            double dq1, double dq2, double& pot, double& psi, double (&fn)[3], double (&fo)[3]) {
     if (kind == 1) {
         {
-            const Pos2 g = pos_geom<true>(dn0, dn1, dn2);
+            const Pos2 g = pos_geom<true, WRAPPED>(dn0, dn1, dn2);
             double v, dv;
             lk2_val_d1<VSM, 0, VSM>(g.k, sbV, v, dv);
             pot += v;
@@ -767,7 +773,7 @@ __device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW,
             fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
         }
         {
-            const Pos2 g = pos_geom<true>(dq0, dq1, dq2);
+            const Pos2 g = pos_geom<true, WRAPPED>(dq0, dq1, dq2);
             double v, dv;
             lk2_val_d1<VSM, 0, VSM>(g.k, sbV, v, dv);
             pot -= v;
@@ -775,10 +781,58 @@ __device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW,
             fo[0] += s * g.d0; fo[1] += s * g.d1; fo[2] += s * g.d2;
         }
     } else {
-        const Pos2 gn = pos_geom<false>(dn0, dn1, dn2);
-        const Pos2 go = pos_geom<false>(dq0, dq1, dq2);
+        const Pos2 gn = pos_geom<false, WRAPPED>(dn0, dn1, dn2);
+        const Pos2 go = pos_geom<false, WRAPPED>(dq0, dq1, dq2);
         pot += lk2_val<VSM, 0, VSM>(gn.k, sbV) - lk2_val<VSM, 0, VSM>(go.k, sbV);
         if (kind == 2) psi += lk2_val<WSM, 1, VSM>(gn.k, sbW) - lk2_val<WSM, 1, VSM>(go.k, sbW);
+    }
+}
+// Partner loop with in-range compaction (PIGS_LOOPV & 512; whole partner range in one warp).  At rcut = L/2 only
+// pi/6 = 52 % of the partners lie inside the cutoff sphere, yet a lane-per-partner loop pays the square root, the
+// table gathers and the force for all of them.  Here a cheap SCAN (minimum image + r^2 of both positions, 30 FP64
+// slots per partner) pushes the pairs that are in range for either position onto a per-warp ring of 64 entries in
+// shared memory (q[6][64]: the six minimum-image components), and the expensive part runs on DENSE batches of 32
+// ring entries.  The moved particle excludes itself by never entering the ring.
+template <bool VSM, bool WSM>
+__device__ __forceinline__ void pair_loop3(int kind, const double* Rx, int ip0, int lane, const double (&xo)[3],
+                                           const double (&xn)[3], Partner cur, double* q, double& pot, double& psi,
+                                           double (&fn)[3], double (&fo)[3]) {
+    const double* p = Rx + pidx(lane);
+    const int nblk = (cP.Np + 31) >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    int qn = 0, qh = 0;
+    for (int blk = 0, j = lane; blk < nblk; ++blk, j += 32) {
+        const double a0 = mimg_fast(xn[0] - cur.x, cP.L[0], cP.invL[0]), a1 = mimg_fast(xn[1] - cur.y, cP.L[1], cP.invL[1]),
+                     a2 = mimg_fast(xn[2] - cur.z, cP.L[2], cP.invL[2]);
+        const double b0 = mimg_fast(xo[0] - cur.x, cP.L[0], cP.invL[0]), b1 = mimg_fast(xo[1] - cur.y, cP.L[1], cP.invL[1]),
+                     b2 = mimg_fast(xo[2] - cur.z, cP.L[2], cP.invL[2]);
+        p += 96;
+        if (blk + 1 < nblk) { cur.x = ldpath(p); cur.y = ldpath(p + PY); cur.z = ldpath(p + PZ); }      // in place, one block ahead
+        const double r2n = a0 * a0 + a1 * a1 + a2 * a2, r2o = b0 * b0 + b1 * b1 + b2 * b2;
+        const bool in = (j < cP.Np) && (j != ip0) && (fmin(r2n, r2o) <= cP.rcut2);
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (in) {
+            double* e = q + ((qh + qn + __popc(m & lt)) & 63);
+            e[0] = a0; e[64] = a1; e[128] = a2; e[192] = b0; e[256] = b1; e[320] = b2;
+        }
+        qn += __popc(m);
+        if (qn >= 32) {
+            __syncwarp();
+            const double* e = q + ((qh + lane) & 63);
+            const double c0 = e[0], c1 = e[64], c2 = e[128], d0 = e[192], d1 = e[256], d2 = e[320];
+            __syncwarp();
+            qh = (qh + 32) & 63; qn -= 32;
+            pair_body2<VSM, WSM, true>(kind, 0u, 0u, c0, c1, c2, d0, d1, d2, pot, psi, fn, fo);
+        }
+    }
+    if (qn > 0) {
+        __syncwarp();
+        const double* e = q + ((qh + lane) & 63);
+        const bool act = lane < qn;
+        const double c0 = act ? e[0] : 1e150, c1 = act ? e[64] : 0.0, c2 = act ? e[128] : 0.0;
+        const double d0 = act ? e[192] : 1e150, d1 = act ? e[256] : 0.0, d2 = act ? e[320] : 0.0;
+        __syncwarp();
+        pair_body2<VSM, WSM, true>(kind, 0u, 0u, c0, c1, c2, d0, d1, d2, pot, psi, fn, fo);
     }
 }
 // partner registers carried from bead to bead by the two-block loop (PIGS_LOOPV & 256): blocks j0 and j0 + jstride of
@@ -869,7 +923,8 @@ __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
 template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
 __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, int j0, int jstride, bool add_self,
                                             const double (&xo)[3], const double (&xn)[3], int lane, double* part,
-                                            const Partner& first, double* lin = nullptr, Carry* cy = nullptr) {
+                                            const Partner& first, double* lin = nullptr, Carry* cy = nullptr,
+                                            double* ring = nullptr) {
     // lin != nullptr (whole partner range in this warp): the part of DeltaS that is LINEAR in the per-lane sums -- the
     // potential and Jastrow terms -- is handed back unreduced in *lin (the caller reduces once per evaluation instead
     // of once per bead); only the Chin force term, quadratic in the reduced force, is reduced here and returned.
@@ -887,7 +942,8 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
             }
         }
     }
-    if (PIGS_LOOPV != 0 && !TRAP && !VPAIR) pair_loop2<VSM, WSM>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo, cy);
+    if ((PIGS_LOOPV & 512) && !TRAP && !VPAIR && ring) pair_loop3<VSM, WSM>(kind, Rx, ip0, lane, xo, xn, first, ring, pot, psi, fn, fo);
+    else if (PIGS_LOOPV != 0 && !TRAP && !VPAIR) pair_loop2<VSM, WSM>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo, cy);
     else pair_loop<TRAP, VSM, WSM, VPAIR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
     if (lin) {
         if (kind == 0) { *lin = cP.wS[ib & 1] * pot; return 0.0; }

@@ -42,7 +42,11 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_loop(const double* slices, in
         int ib = KINDSEL == 0 ? 2 : (KINDSEL == 1 ? 3 : (KINDSEL == 2 ? 0 : 1 + (int)((h >> 20) % 29)));
         double xo[3] = {Rx[pidx(ip0)], Rx[pidx(ip0) + PY], Rx[pidx(ip0) + PZ]};
         double xn[3] = {xo[0] + 0.05, xo[1] - 0.03, xo[2] + 0.02};
-#if PIGS_LOOPV & 256
+#if PIGS_LOOPV & 512
+        if (lane < cP.Np) first = load_partner(Rx, lane);
+        acc += bead_eval<false, true, true, false>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn, lane, nullptr, first, nullptr, nullptr,
+                                                   pigs_smem_base + 2 * ntab + (threadIdx.x >> 5) * 384);
+#elif PIGS_LOOPV & 256
         if (it == 0) { cy.a = load_partner(Rx, lane); if (lane + 32 < cP.Np) cy.b = load_partner(Rx, lane + 32); }
         cy.next = slices + (size_t)(((h * 1664525u + 1013904223u) >> 8) % nslices) * ss;      // the slice of the next iteration
         acc += bead_eval<false, true, true, false>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn, lane, nullptr, first, nullptr, &cy);
@@ -74,7 +78,7 @@ int main(int argc, char** argv) {
     cudaMemcpy(d_sl, slices.data(), slices.size() * 8, cudaMemcpyHostToDevice);
     P.vtab = d_tab; P.logwf = d_tab;
     cudaMemcpyToSymbol(cP, &P, sizeof P);
-    size_t smem = 2 * 10006 * 8;
+    size_t smem = 2 * 10006 * 8 + 16 * 384 * 8;
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     auto run = [&](auto kern, const char* name) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
