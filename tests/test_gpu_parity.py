@@ -495,6 +495,40 @@ def test_multi_gpu_handle_equals_single_gpu(rng, monkeypatch):
     assert np.array_equal(one.get_state(5)[0], two.get_state(5)[0])          # per-chain routing
 
 
+@pytest.mark.parametrize("rng,schedule", [("philox", 0), ("philox", 1), ("mt", 0)])
+def test_chain_checkpoint_continues_on_another_gpu_count(rng, schedule, tmp_path, monkeypatch):
+    """pigs_save_checkpoint / pigs_load_checkpoint (the multi-chain extension of CheckPoint, vpi_mod.f90:263-309, and of
+    mtsave/mtget, random_mod.f90:125-191): the file holds the chains in global order, so a run saved by a one-GPU handle
+    continues bit for bit in a FRESH two-GPU handle and the other way round -- paths, worm state, permutation
+    histograms and every random stream (Philox counters of the chain and of its window workers, MT19937 states)."""
+    from pathintegralgroundstate_b200.host import PigsError
+    cfg, n = CWX, 6
+    def fresh(gpus):
+        try:
+            return _fresh(cfg, n, 17, rng=rng, schedule=schedule, gpus=gpus)
+        except PigsError:                           # a one-GPU box: both shards on the same device
+            monkeypatch.setenv("PIGS_MULTI_SAME_DEVICE", "1")
+            return _fresh(cfg, n, 17, rng=rng, schedule=schedule, gpus=gpus)
+    for g_save, g_load in ((1, 2), (2, 1)):
+        a = fresh(g_save)
+        a.run_block(5)
+        f = tmp_path / f"ck_{g_save}.bin"
+        a.save_checkpoint(f)
+        a.run_block(5)                              # the uninterrupted continuation
+        b = fresh(g_load)
+        b.run_block(2)                              # something else happened in this handle before the restore
+        b.load_checkpoint(f)
+        b.run_block(5)
+        _same_chains(a.get_block_chains(), b.get_block_chains())
+        for x, y in zip(a.get_state_all(), b.get_state_all()):
+            assert np.array_equal(x, y)
+        for c in (0, n - 1):
+            pa, pb = a.get_perm(c), b.get_perm(c)
+            assert all(np.array_equal(u, v) for u, v in zip(pa, pb))
+    with pytest.raises(PigsError):                  # a file of another configuration is refused
+        _fresh(CW, 3, 1).load_checkpoint(f)
+
+
 def test_two_handles_on_one_device_do_not_disturb_each_other():
     """an asynchronous block of handle A is still running when handle B uploads ITS parameters and launches: both
     must give what they give alone (the launch path waits for the other handle's kernel before touching the
