@@ -938,8 +938,9 @@ extern "C" int pigs_update_action(pigs_handle h, int n, const double* R, const i
     MULTI(h, pigs_update_action(h->sub[0], n, R, ip, ib, xnew, xold, DeltaS));
     NEED(h);
     if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
-    if (n < 0 || !R || !ip || !ib || !xnew || !xold || !DeltaS) return fail(PIGS_E_ARG, "bad argument");
-    if (n == 0) return PIGS_OK;
+    if (n < 0) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;                    // an empty request: nothing to read, nothing to launch
+    if (!R || !ip || !ib || !xnew || !xold || !DeltaS) return fail(PIGS_E_ARG, "bad argument");
     const DevParams& P = h->P;
     for (int i = 0; i < n; ++i)
         if (ip[i] < 1 || ip[i] > P.Np || ib[i] < 0 || ib[i] > 2 * P.Nb) return fail(PIGS_E_ARG, "ip/ib out of range");
@@ -989,8 +990,9 @@ extern "C" int pigs_local_energy(pigs_handle h, int n, const double* R, double* 
     MULTI(h, pigs_local_energy(h->sub[0], n, R, E, Kin, Pot));
     NEED(h);
     if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
-    if (n < 0 || !R) return fail(PIGS_E_ARG, "bad argument");
-    if (n == 0) return PIGS_OK;
+    if (n < 0) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;                    // an empty request: nothing to read, nothing to launch
+    if (!R) return fail(PIGS_E_ARG, "bad argument");
     std::vector<double> soa, out((size_t)3 * n);
     to_soa(h->P, n, R, soa);
     int rc = unit_call(h, U_LOCAL_ENERGY, n, soa, 3, nullptr, out.data());
@@ -1002,8 +1004,9 @@ extern "C" int pigs_therm_energy(pigs_handle h, int n, const double* Path, doubl
     MULTI(h, pigs_therm_energy(h->sub[0], n, Path, E, Ec, Ep));
     NEED(h);
     if (!h->tables_set) return fail(PIGS_E_STATE, "pigs_set_tables has not been called");
-    if (n < 0 || !Path) return fail(PIGS_E_ARG, "bad argument");
-    if (n == 0) return PIGS_OK;
+    if (n < 0) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;                    // an empty request: nothing to read, nothing to launch
+    if (!Path) return fail(PIGS_E_ARG, "bad argument");
     std::vector<double> soa, out((size_t)3 * n);
     to_soa(h->P, (long long)n * h->P.S, Path, soa);
     int rc = unit_call(h, U_THERM_ENERGY, n, soa, 3, nullptr, out.data());
@@ -1015,8 +1018,9 @@ extern "C" int pigs_pair_correlation(pigs_handle h, int n, const double* R, doub
     MULTI(h, pigs_pair_correlation(h->sub[0], n, R, gr));
     NEED(h);
     if (h->P.trap) return fail(PIGS_E_ARG, "PairCorrelation is not defined in trap mode (vpi.f90:466)");
-    if (n < 0 || !R || !gr) return fail(PIGS_E_ARG, "bad argument");
-    if (n == 0) return PIGS_OK;
+    if (n < 0) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;                    // an empty request: nothing to read, nothing to launch
+    if (!R || !gr) return fail(PIGS_E_ARG, "bad argument");
     std::vector<double> soa;
     to_soa(h->P, n, R, soa);
     return unit_call(h, U_PAIR_CORR, n, soa, h->P.Nbin, gr, gr);
@@ -1025,8 +1029,9 @@ extern "C" int pigs_structure_factor(pigs_handle h, int n, const double* R, doub
     MULTI(h, pigs_structure_factor(h->sub[0], n, R, Sk));
     NEED(h);
     if (h->P.trap) return fail(PIGS_E_ARG, "StructureFactor is not defined in trap mode (vpi.f90:466)");
-    if (n < 0 || !R || !Sk) return fail(PIGS_E_ARG, "bad argument");
-    if (n == 0) return PIGS_OK;
+    if (n < 0) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;                    // an empty request: nothing to read, nothing to launch
+    if (!R || !Sk) return fail(PIGS_E_ARG, "bad argument");
     std::vector<double> soa;
     to_soa(h->P, n, R, soa);
     return unit_call(h, U_SOFK, n, soa, (size_t)h->P.Nk * h->P.dim, Sk, Sk);
@@ -1035,8 +1040,9 @@ extern "C" int pigs_obdm(pigs_handle h, int n, const double* xend, double* nrho)
     MULTI(h, pigs_obdm(h->sub[0], n, xend, nrho));
     NEED(h);
     if (h->P.trap) return fail(PIGS_E_ARG, "OBDM is not defined in trap mode (vpi.f90:400)");
-    if (n < 0 || !xend || !nrho) return fail(PIGS_E_ARG, "bad argument");
-    if (n == 0) return PIGS_OK;
+    if (n < 0) return fail(PIGS_E_ARG, "bad argument");
+    if (n == 0) return PIGS_OK;                    // an empty request: nothing to read, nothing to launch
+    if (!xend || !nrho) return fail(PIGS_E_ARG, "bad argument");
     const int dim = h->P.dim;
     std::vector<double> xe((size_t)n * 6, 0.0);
     for (int c = 0; c < n; ++c) for (int j = 0; j < 2; ++j) for (int k = 0; k < dim; ++k) xe[(size_t)c * 6 + j * 3 + k] = xend[((size_t)c * 2 + j) * dim + k];

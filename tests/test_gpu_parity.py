@@ -617,3 +617,41 @@ def test_update_action_shared_memory_tables(name, cfg):
     ref = np.array([o.update_action(int(ips[i]), int(ibs[i]), xnew[i], xold[i], R=R[i]) for i in range(n)])
     got = g.update_action(R, ips, ibs, xnew, xold)
     assert close(got, ref), f"{name}: worst {worst(got, ref):.3e}"
+
+
+# ------------------------------------------------------------------ the edges of the parameter space
+@pytest.mark.parametrize("name,cfg", [
+    ("two particles: one partner per bead", dict(CWX, Np=2, density=0.02, Nk=4)),
+    ("one particle past a 32-lane partner block", dict(CWX, Np=33)),
+    ("the longest path the kernel takes: Nb = 65, 131 slices", dict(CW, Nb=65, Lstag=20, Nlev=4)),
+    ("one dimension", dict(CWX, dim=1, density=0.3, Np=12)),
+])
+def test_edge_shapes_replay(name, cfg):
+    _replay_block(cfg, nchain=2, nstep=3, nblock=2)
+
+
+def test_refused_shapes():
+    from pathintegralgroundstate_b200.host import PigsError
+    for bad, msg in ((dict(CW, Nb=66), "Nb too large"), (dict(CW, Np=1), "Np>=2"), (dict(CW, Lstag=9), "Lstag"),
+                     (dict(CW, Nlev=5), "Nlev")):
+        with pytest.raises(PigsError, match=msg):
+            PigsCuda(bad, n_chains=1)
+
+
+def test_empty_requests_are_no_ops():
+    """zero evaluations / zero steps: nothing is launched for the unit entries, a zero-step block leaves every chain
+    where it was and reports an all-zero block (the reference's `do istep=1,0` runs no iteration)"""
+    g = _fresh(CW, 3, 5)
+    before = g.get_state_all()
+    n0 = g.launches() if hasattr(g, "launches") else None
+    Np = CW["Np"]
+    out = g.update_action(np.zeros((0, Np, 3)), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 3)), np.zeros((0, 3)))
+    assert np.asarray(out).shape == (0,)
+    E = g.local_energy(np.zeros((0, Np, 3)))
+    assert all(np.asarray(x).size == 0 for x in E)
+    g.run_block(0)
+    b, gr, Sk, nr = g.get_block()
+    assert all(int(b[k]) == 0 for k in INT_KEYS) and all(float(b[k]) == 0.0 for k in SUM_KEYS)
+    assert not gr.any() and not nr.any() and not np.asarray(Sk).any()
+    for x, y in zip(before, g.get_state_all()):
+        assert np.array_equal(x, y)
