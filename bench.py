@@ -235,6 +235,11 @@ def run_ours(args, cfg):
             b = sim.get_block()[0]
         upd_cls += np.array(b["bead_updates"], dtype=float)
         kernel_ms += sim.last_block_ms()
+        if not (np.isfinite(b["sumE"]) and np.isfinite(b["sumEt"]) and b["idiag_block"] > 0):
+            raise SystemExit(f"bench: the block result is not finite (sumE {b['sumE']}, sumEt {b['sumEt']}): refusing to time garbage")
+    last_block = {"E_per_particle_mixed": float(b["sumE"]) / max(int(b["idiag_block"]), 1) / cfg["Np"],
+                  "E_per_particle_thermodynamic": float(b["sumEt"]) / max(int(b["idiag_block"]), 1) / cfg["Np"],
+                  "diagonal_samples": int(b["idiag_block"])}
     ev1.record(lib_stream)
     barrier()
     wall = time.perf_counter() - t0
@@ -312,6 +317,7 @@ def run_ours(args, cfg):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
                 "d2h_bytes_per_step": state_bytes + nvec * 8},
         "gpu_launches": int(launches),
+        "last_block": last_block,
         "roofline": roofline,
         "wall_ms_per_step": wall_ms / args.steps,
     }

@@ -658,7 +658,7 @@ PIGS_PRAGMA_UNROLL
 //       dense is one serial chain per block, and the loop is latency-bound, not slot-bound.  Off.
 // Variants 1 and 32 give results bit-identical to variant 0.
 #ifndef PIGS_LOOPV
-#define PIGS_LOOPV 33
+#define PIGS_LOOPV 1057
 #endif
 
 // d - L*q with q = -1, 0, +1 decided on the HIGH WORD of d: |d| > L/2 is judged with a resolution of 2^-20
@@ -854,6 +854,23 @@ __device__ __forceinline__ void pair_loop2(int kind, const double* Rx, int ip0, 
         sbV = (unsigned)__cvta_generic_to_shared(pigs_smem_base);
         sbW = sbV + (unsigned)cP.tabW_off;
     }
+    if ((PIGS_LOOPV & 1024) && cy) {
+        // one block per iteration, partner registers carried from bead to bead: after its last use in this bead the
+        // register triple is reloaded with the first block of the next evaluated slice (no separate preload, no copy)
+        Partner a = cy->a;
+        const double* pn = cy->next ? cy->next + pidx(j0) : nullptr;
+        for (int left = cP.Np - j0; left > 0; left -= jstride) {
+            if (left == self_left) a.x = 1e150;
+            const double dn0 = xn[0] - a.x, dn1 = xn[1] - a.y, dn2 = xn[2] - a.z;
+            const double dq0 = xo[0] - a.x, dq1 = xo[1] - a.y, dq2 = xo[2] - a.z;
+            p += pstep;
+            if (left > jstride) { a.x = ldpath(p); a.y = ldpath(p + PY); a.z = ldpath(p + PZ); }
+            else if (pn) { a.x = ldpath(pn); a.y = ldpath(pn + PY); a.z = ldpath(pn + PZ); }
+            pair_body2<VSM, WSM>(kind, sbV, sbW, dn0, dn1, dn2, dq0, dq1, dq2, pot, psi, fn, fo);
+        }
+        cy->a = a;
+        return;
+    }
     if ((PIGS_LOOPV & 256) && cy) {
         // Two partner blocks per iteration: four independent dependency chains per warp instead of two.  The partner
         // registers are a stream that runs across beads: after their last use in a bead they are reloaded with the
@@ -948,14 +965,15 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
     if (lin) {
         if (kind == 0) { *lin = cP.wS[ib & 1] * pot; return 0.0; }
         if (kind == 2) { *lin = fma(cP.wS[2], pot, -psi); return 0.0; }
-        *lin = cP.wS[1] * pot;
         const double a6[8] = {0.0, 0.0, fn[0], fn[1], fn[2], fo[0], fo[1], fo[2]};
-        const double v6 = warp_sum8(a6, lane);
+        const double v6 = warp_sum8(a6, lane);          // quad q holds the complete sum of value q
         const int q6 = lane >> 2;
         const double c6 = cP.cF;
-        double t6 = (q6 < 2) ? 0.0 : ((q6 < 5) ? c6 * v6 * v6 : -c6 * v6 * v6);
-        t6 += shx(t6, 4); t6 += shx(t6, 8); t6 += shx(t6, 16);
-        return t6;
+        // +-cF F^2 is quadratic in the reduced force, but the SUM of the six squares over the quads is linear again:
+        // one lane per quad adds its square to the deferred part (three shuffle levels less per odd bead)
+        const double t6 = (q6 < 2 || (lane & 3) != 0) ? 0.0 : ((q6 < 5) ? c6 * v6 * v6 : -c6 * v6 * v6);
+        *lin = fma(cP.wS[1], pot, t6);
+        return 0.0;
     }
     if (kind == 0) {
         double v = warp_sum(pot);

@@ -84,7 +84,7 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         // decomposition, no partial-sum exchange
         const int lane = G.lane;
         const bool have = lane < cP.Np;
-        constexpr bool TWO = (PIGS_LOOPV & 256) && !PIGS_TRAP && !PIGS_VPAIR;      // two-block partner loop, see pair_loop2
+        constexpr bool TWO = (PIGS_LOOPV & (256 | 1024)) && !PIGS_TRAP && !PIGS_VPAIR;      // carried partner stream, see pair_loop2
         Partner first;
         Carry cy;
         first.x = first.y = first.z = 0.0;
@@ -92,7 +92,7 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         const double* Rx = slice(gs, b0);                                  // walks the evaluated slices
         const long long sstride = (long long)bstride * 3 * cP.NpS, pfoff = (long long)cA.pfdist * sstride;
         if (have) first = load_partner(Rx, lane);
-        if (TWO) { cy.a = first; if (lane + 32 < cP.Np) cy.b = load_partner(Rx, lane + 32); }
+        if (TWO) { cy.a = first; if ((PIGS_LOOPV & 256) && lane + 32 < cP.Np) cy.b = load_partner(Rx, lane + 32); }
         double Sw = 0.0, Slin = 0.0;       // Slin: per-lane sum of the terms linear in the pair sums, reduced once below
         for (int m = 0; m < nb; ++m, Rx += sstride) {
             const int ib = b0 + m * bstride;
