@@ -340,8 +340,18 @@ __device__ __forceinline__ double mimg_lt_first(double d, double L, double Lh) {
 // Hot-loop form: d - L*rint(d/L) with rint() by the 2^52 trick (3 FP64 issue
 // slots instead of 4 + 4 selects).  Identical to mimg() for |d| < 1.5 L except
 // exactly at |d| = L/2, where either image gives the same r^2.
+// 1.5 * 2^52: adding and subtracting it rounds to the nearest integer.  (Keeping it in a register pair so that 1/L
+// could be a constant-bank operand of the FMA instead of an LDC per iteration is not expressible: ptxas folds any
+// materialisation of the constant back into an immediate.)
+__device__ __forceinline__ double magic52() { return 6755399441055744.0; }
 __device__ __forceinline__ double mimg_fast(double d, double L, double invL) {
-    const double MAGIC = 6755399441055744.0;
+#if defined(PIGS_MIMG_FRND)
+    // FRND.F64 on the conversion pipe: 2 FP64 slots instead of 3 and no magic constant (-12 FP64 instructions per
+    // partner, no LDC of 1/L per iteration) -- measured 1.3 % SLOWER in the sweep kernel (C3 467 -> 461 M), 2.5 %
+    // slower in the isolated loop: FRND's latency is longer than the DADD it replaces.  Kept as a build option.
+    return fma(-rint(d * invL), L, d);
+#endif
+    const double MAGIC = magic52();
     double q = fma(d, invL, MAGIC) - MAGIC;
     return fma(-q, L, d);
 }
@@ -718,7 +728,7 @@ __device__ __forceinline__ Pos2 pos_geom(double d0, double d1, double d2) {
         double r;
         if (NEED_IR) { if (PIGS_LOOPV & 16) rsqrt_sqrt_q(r2, g.ir, r); else { g.ir = rsqrt_pos(r2); r = r2 * g.ir; } }
         else { g.ir = 0.0; r = (PIGS_LOOPV & 16) ? sqrt_q(r2) : sqrt_pos(r2); }
-        const double MAGIC = 6755399441055744.0;
+        const double MAGIC = magic52();
         const double m = __fma_rd(r, cP.inv_dr, MAGIC);
         g.k.i0 = in ? max(__double2loint(m), 1) : cP.Nmax + 3;     // i0 >= 1: the centred difference reads F(i0-1) (r < dr never survives a Metropolis test)
         g.k.t = fma(r, cP.inv_dr, -(m - MAGIC));
