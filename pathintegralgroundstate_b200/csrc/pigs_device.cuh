@@ -137,6 +137,7 @@ struct GS {
     const double* tabV;  // table bases: shared-memory copies when staged, else global
     const double* tabW;
     double bc[8];        // broadcast slots
+    double kc[4];        // 1/L[0..2], 1/dr: the partner loop's constants as plain data (PIGS_KC)
     double eacc[NE];
     long long cnt[NCNT];
     int ibc[8];
@@ -670,6 +671,10 @@ PIGS_PRAGMA_UNROLL
 #ifndef PIGS_LOOPV
 #define PIGS_LOOPV 1057
 #endif
+#ifndef PIGS_KC
+#define PIGS_KC 1
+#endif
+#define PIGS_EXPL_LDS (PIGS_LOOPV & 8)
 
 // d - L*q with q = -1, 0, +1 decided on the HIGH WORD of d: |d| > L/2 is judged with a resolution of 2^-20
 // relative.  A component inside the band (L/2, L/2 (1 + 2^-20)] keeps the far image; such a pair lies beyond the
@@ -687,6 +692,16 @@ __device__ __forceinline__ double mimg_hi(double d, double L, float LhF) {
     const int qhi = (fabsf(__int_as_float(hi)) > LhF) ? one : 0;
     return fma(-__hiloint2double(qhi, 0), L, d);
 }
+// The four constants at the head of every partner's dependency chain, as REGISTER values.  Read from the constant
+// bank they are re-fetched with an LDC in every loop iteration (ptxas rematerialises them under register
+// pressure); read once per evaluation from the group's shared-memory block they cannot be rematerialised: -10 LDC,
+// C3 +0.6 %, C2 +0.7 %, C5 +0.9 %.  Going further was measured and LOSES: L[0..2] and rcut^2 as well (-6 LDCU) -2.9 %,
+// plus the tables' shared addresses and the zero-tail index (-8 uniform-datapath instructions, loop 242 -> 218
+// instructions) -3.6 %: the registers they occupy cost more than the instructions they save
+// (profiles/bench_r02_loop_constants_ab.log).
+struct LoopK {
+    double iL0, iL1, iL2, idr;
+};
 struct Pos2 {          // geometry of one position against one partner
     double d0, d1, d2, ir;
     Lk k;
@@ -711,14 +726,18 @@ __device__ __forceinline__ void rsqrt_sqrt_q(double x, double& ir, double& r) {
     r = fma(0.5 * r0, e, r0);
 }
 template <bool NEED_IR, bool WRAPPED = false>
-__device__ __forceinline__ Pos2 pos_geom(double d0, double d1, double d2) {
+__device__ __forceinline__ Pos2 pos_geom(double d0, double d1, double d2, const LoopK* K = nullptr) {
     Pos2 g;
+    const double inv_dr = K ? K->idr : cP.inv_dr;
     if (WRAPPED) {                   // the components are minimum-image components already
         g.d0 = d0; g.d1 = d1; g.d2 = d2;
     } else if (PIGS_LOOPV & 4) {
         g.d0 = mimg_hi(d0, cP.L[0], cP.LhF[0]); g.d1 = mimg_hi(d1, cP.L[1], cP.LhF[1]); g.d2 = mimg_hi(d2, cP.L[2], cP.LhF[2]);
     } else {
-        g.d0 = mimg_fast(d0, cP.L[0], cP.invL[0]); g.d1 = mimg_fast(d1, cP.L[1], cP.invL[1]); g.d2 = mimg_fast(d2, cP.L[2], cP.invL[2]);
+        {
+        g.d0 = mimg_fast(d0, cP.L[0], K ? K->iL0 : cP.invL[0]); g.d1 = mimg_fast(d1, cP.L[1], K ? K->iL1 : cP.invL[1]);
+        g.d2 = mimg_fast(d2, cP.L[2], K ? K->iL2 : cP.invL[2]);
+        }
     }
     const double r2 = g.d0 * g.d0 + g.d1 * g.d1 + g.d2 * g.d2;
     if (PIGS_LOOPV & 32) {
@@ -729,9 +748,9 @@ __device__ __forceinline__ Pos2 pos_geom(double d0, double d1, double d2) {
         if (NEED_IR) { if (PIGS_LOOPV & 16) rsqrt_sqrt_q(r2, g.ir, r); else { g.ir = rsqrt_pos(r2); r = r2 * g.ir; } }
         else { g.ir = 0.0; r = (PIGS_LOOPV & 16) ? sqrt_q(r2) : sqrt_pos(r2); }
         const double MAGIC = magic52();
-        const double m = __fma_rd(r, cP.inv_dr, MAGIC);
-        g.k.i0 = in ? max(__double2loint(m), 1) : cP.Nmax + 3;     // i0 >= 1: the centred difference reads F(i0-1) (r < dr never survives a Metropolis test)
-        g.k.t = fma(r, cP.inv_dr, -(m - MAGIC));
+        const double m = __fma_rd(r, inv_dr, MAGIC);
+        g.k.i0 = in ? max(__double2loint(m), 1) : cP.Nmax + 3;
+        g.k.t = fma(r, inv_dr, -(m - MAGIC));
         return g;
     }
     const double r2c = (r2 <= cP.rcut2) ? r2 : cP.rclamp2;        // beyond the cutoff, poisoned or NaN: zero tail (Q24)
@@ -746,7 +765,7 @@ __device__ __forceinline__ Pos2 pos_geom(double d0, double d1, double d2) {
 }
 template <bool SM, int WHICH, bool VF>
 __device__ __forceinline__ double lk2_val(const Lk& k, unsigned sb) {
-    if (SM && (PIGS_LOOPV & 8)) {
+    if (SM && PIGS_EXPL_LDS) {
         const unsigned a = sb + ((unsigned)k.i0 << 3);
         double f0, f1;
         asm("ld.shared.f64 %0, [%1];" : "=d"(f0) : "r"(a));
@@ -757,7 +776,7 @@ __device__ __forceinline__ double lk2_val(const Lk& k, unsigned sb) {
 }
 template <bool SM, int WHICH, bool VF>
 __device__ __forceinline__ void lk2_val_d1(const Lk& k, unsigned sb, double& v, double& d1) {
-    if (SM && (PIGS_LOOPV & 8)) {
+    if (SM && PIGS_EXPL_LDS) {
         const unsigned a = sb + ((unsigned)k.i0 << 3);
         double fm, f0, f1, f2;
         asm("ld.shared.f64 %0, [%1+-8];" : "=d"(fm) : "r"(a));
@@ -772,10 +791,11 @@ __device__ __forceinline__ void lk2_val_d1(const Lk& k, unsigned sb, double& v, 
 // both positions of the displaced bead against ONE partner; dn/dq = x_new - r_j, x_old - r_j before the minimum image
 template <bool VSM, bool WSM, bool WRAPPED = false>
 __device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW, double dn0, double dn1, double dn2, double dq0,
-                                           double dq1, double dq2, double& pot, double& psi, double (&fn)[3], double (&fo)[3]) {
+                                           double dq1, double dq2, double& pot, double& psi, double (&fn)[3], double (&fo)[3],
+                                           const LoopK* K = nullptr) {
     if (kind == 1) {
         {
-            const Pos2 g = pos_geom<true, WRAPPED>(dn0, dn1, dn2);
+            const Pos2 g = pos_geom<true, WRAPPED>(dn0, dn1, dn2, K);
             double v, dv;
             lk2_val_d1<VSM, 0, VSM>(g.k, sbV, v, dv);
             pot += v;
@@ -783,7 +803,7 @@ __device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW,
             fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
         }
         {
-            const Pos2 g = pos_geom<true, WRAPPED>(dq0, dq1, dq2);
+            const Pos2 g = pos_geom<true, WRAPPED>(dq0, dq1, dq2, K);
             double v, dv;
             lk2_val_d1<VSM, 0, VSM>(g.k, sbV, v, dv);
             pot -= v;
@@ -791,8 +811,8 @@ __device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW,
             fo[0] += s * g.d0; fo[1] += s * g.d1; fo[2] += s * g.d2;
         }
     } else {
-        const Pos2 gn = pos_geom<false, WRAPPED>(dn0, dn1, dn2);
-        const Pos2 go = pos_geom<false, WRAPPED>(dq0, dq1, dq2);
+        const Pos2 gn = pos_geom<false, WRAPPED>(dn0, dn1, dn2, K);
+        const Pos2 go = pos_geom<false, WRAPPED>(dq0, dq1, dq2, K);
         pot += lk2_val<VSM, 0, VSM>(gn.k, sbV) - lk2_val<VSM, 0, VSM>(go.k, sbV);
         if (kind == 2) psi += lk2_val<WSM, 1, VSM>(gn.k, sbW) - lk2_val<WSM, 1, VSM>(go.k, sbW);
     }
@@ -850,6 +870,7 @@ __device__ __forceinline__ void pair_loop3(int kind, const double* Rx, int ip0, 
 struct Carry {
     Partner a, b;
     const double* next;
+    const LoopK* K;
 };
 template <bool VSM, bool WSM>
 __device__ __forceinline__ void pair_loop2(int kind, const double* Rx, int ip0, int j0, int jstride, const double (&xo)[3],
@@ -859,7 +880,7 @@ __device__ __forceinline__ void pair_loop2(int kind, const double* Rx, int ip0, 
     const int pstep = 3 * jstride;
     const int self_left = cP.Np - ip0;
     unsigned sbV = 0, sbW = 0;
-    if (PIGS_LOOPV & 8) {
+    if (PIGS_EXPL_LDS) {
         extern __shared__ __align__(16) double pigs_smem_base[];
         sbV = (unsigned)__cvta_generic_to_shared(pigs_smem_base);
         sbW = sbV + (unsigned)cP.tabW_off;
@@ -876,7 +897,7 @@ __device__ __forceinline__ void pair_loop2(int kind, const double* Rx, int ip0, 
             p += pstep;
             if (left > jstride) { a.x = ldpath(p); a.y = ldpath(p + PY); a.z = ldpath(p + PZ); }
             else if (pn) { a.x = ldpath(pn); a.y = ldpath(pn + PY); a.z = ldpath(pn + PZ); }
-            pair_body2<VSM, WSM>(kind, sbV, sbW, dn0, dn1, dn2, dq0, dq1, dq2, pot, psi, fn, fo);
+            pair_body2<VSM, WSM>(kind, sbV, sbW, dn0, dn1, dn2, dq0, dq1, dq2, pot, psi, fn, fo, cy->K);
         }
         cy->a = a;
         return;

@@ -88,7 +88,13 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
         Partner first;
         Carry cy;
         first.x = first.y = first.z = 0.0;
-        cy.a = first; cy.b = first;
+        cy.a = first; cy.b = first; cy.K = nullptr;
+#if PIGS_KC >= 1
+        LoopK K;
+        { const volatile double* kc = gs->kc; K.iL0 = kc[0]; K.iL1 = kc[1]; K.iL2 = kc[2]; K.idr = kc[3];
+        }
+        cy.K = &K;
+#endif
         const double* Rx = slice(gs, b0);                                  // walks the evaluated slices
         const long long sstride = (long long)bstride * 3 * cP.NpS, pfoff = (long long)cA.pfdist * sstride;
         if (have) first = load_partner(Rx, lane);
@@ -1261,6 +1267,7 @@ PIGS_T __device__ __forceinline__ void sweep_body() {
             b->pp = cP.pp + (size_t)c * cP.Np;
             b->tabV = tV; b->tabW = tW;
             b->chain = c + cP.chain_offset;
+            b->kc[0] = cP.invL[0]; b->kc[1] = cP.invL[1]; b->kc[2] = cP.invL[2]; b->kc[3] = cP.inv_dr;
             b->gsize = tid == 0 ? T : 32; b->gshift = tid == 0 ? cA.tshift : 5; b->gbar = g;
         }
         if (tid == 0) {

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_loop(const double* slices, in
     double acc = 0.0;
     const size_t ss = (size_t)3 * cP.NpS;
     Partner first; first.x = first.y = first.z = 0.0;
-    Carry cy; cy.a = first; cy.b = first; cy.next = nullptr;
+    Carry cy; cy.a = first; cy.b = first; cy.next = nullptr; cy.K = nullptr;
     for (int it = 0; it < iters; ++it) {
         h = h * 1664525u + 1013904223u;
         int s = (h >> 8) % nslices;
