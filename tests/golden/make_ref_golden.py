@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import pigs_ref                                    # noqa: E402
-from tests.common import C1, C2, CW, CWX, CS, oracle_cfg       # noqa: E402
+from tests.common import C1, C2, C3, CREF, CW, CWX, CS, oracle_cfg       # noqa: E402
 
 
 def main():
@@ -34,7 +34,8 @@ def main():
     r.sgrnd(1982)
     G["stream"] = dict(cfg=oracle_cfg(CW), seed=1982, grnd=[r.grnd().hex() for _ in range(1300)],
                        rangauss=[r.rangauss().hex() for _ in range(300)])
-    for name, cfg, Nblock, Nstep in (("CW", CW, 4, 25), ("CWX", CWX, 5, 25), ("CS", CS, 3, 20), ("C1", C1, 2, 10), ("C2", C2, 2, 2)):
+    for name, cfg, Nblock, Nstep in (("CW", CW, 4, 25), ("CWX", CWX, 5, 25), ("CS", CS, 3, 20), ("C1", C1, 2, 10), ("C2", C2, 2, 2),
+                                     ("CREF", CREF, 2, 3), ("C3", C3, 2, 2)):      # the shipped vpi.in; the benchmarked size
         c = oracle_cfg(cfg)
         rr = pigs_ref.Ref(c, Nblock=Nblock, Nstep=Nstep)
         G["program"].append(dict(name=name, cfg=c, Nblock=Nblock, Nstep=Nstep,
