@@ -655,7 +655,7 @@ PIGS_PRAGMA_UNROLL
 //   1   partner registers reloaded IN PLACE right after their last use (no cur/nxt copy: -9 MOV, -6 registers);
 //       the moved particle excludes itself through a poisoned x coordinate (r^2 ~ 1e268 -> zero tail of the
 //       tables) instead of two selects per position                                         640 / 684
-//   32  + the cutoff acts on the table INDEX, off the critical path (sqrt of the unclamped r^2)     648 / 695   <- default
+//   32  + the cutoff acts on the table INDEX, off the critical path (sqrt of the unclamped r^2)     648 / 695   <- on
 //   16  + one Newton step instead of the three-term step (1e-12 in r): +0.7 %, not worth the digits   652 / 703
 //   4   wrap count of the minimum image from a compare on the high word of d: -12 FP64 slots, +10 ALU   635 / 678 (slower)
 //   8   table reads through explicit ld.shared with a 32-bit base: no change
@@ -667,7 +667,10 @@ PIGS_PRAGMA_UNROLL
 //       per-warp shared-memory ring and get the square root / table / force part in dense batches of 32): FP64 slots
 //       per bead-update -25 %, yet 716 -> 559 (L2), 528 -> 466 (HBM), N=64 1633 -> 1306: scan -> ballot -> ring ->
 //       dense is one serial chain per block, and the loop is latency-bound, not slot-bound.  Off.
-// Variants 1 and 32 give results bit-identical to variant 0.
+//   1024 one block per iteration, partner registers CARRIED from bead to bead: after their last use in a bead they
+//       are reloaded with the first block of the next evaluated slice (no preload in the bead loop, no copy): in the
+//       sweep kernel C3 455 -> 461 M, C2 898 -> 914 M                                                    <- on
+// Default 1057 = 1 + 32 + 1024.  Variants 1, 32 and 1024 give results bit-identical to variant 0.
 #ifndef PIGS_LOOPV
 #define PIGS_LOOPV 1057
 #endif
