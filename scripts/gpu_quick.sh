@@ -9,9 +9,6 @@ run --workload C2 --mc-steps 8
 run --workload C5 --chains 4096 --mc-steps 8
 run --workload C5 --chains 512 --schedule 1 --mc-steps 20
 PIGS_PREFETCH=0 run --workload C3
-PIGS_CUDA_LIB=$PWD/pathintegralgroundstate_b200/libpigs_cuda_640.so run --workload C3 --chains 2960
-PIGS_CUDA_LIB=$PWD/pathintegralgroundstate_b200/libpigs_cuda_768.so run --workload C3 --chains 3552
-PIGS_CUDA_LIB=$PWD/pathintegralgroundstate_b200/libpigs_cuda_640.so run --workload C2 --chains 2960 --mc-steps 8
 } > gpurun_out/r2_quick.log 2>&1
 cat gpurun_out/r2_quick.log; tail -3 gpurun_out/r2_quick.err
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
