@@ -185,7 +185,7 @@ def run_ours(args, cfg):
         n_chains = args.chains
         first, _ = shard_chains(n_chains * world, rank, world)
 
-    sim = PigsCuda(cfg, n_chains=n_chains, rng="philox", seed=SEED, chain_offset=first, device=local, schedule=args.schedule)
+    sim = PigsCuda(cfg, n_chains=n_chains, rng=args.rng, seed=SEED, chain_offset=first, device=local, schedule=args.schedule)
     sim.fill_tables("hfdb")
     P, xe = synthetic_paths(cfg, n_chains, seed=SEED + 7919 * rank)
     # pinned host buffers of the chains' state (the e2e leg copies them every step)
@@ -309,7 +309,7 @@ def run_ours(args, cfg):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "schedule": sim.schedule_name(), "Np": cfg["Np"], "Nb": cfg["Nb"], "chains_per_gpu": n_chains,
-                   "mc_steps_per_step": nstep, "rng": "philox", "worm": "on (CWorm=0.5, Nobdm=10, swap)",
+                   "mc_steps_per_step": nstep, "rng": args.rng, "worm": "on (CWorm=0.5, Nobdm=10, swap)",
                    "estimators": "mixed+thermodynamic energy, g(r), S(k), OBDM",
                    "l2": f"inputs larger than L2: {state_bytes / 1e6:.0f} MB of paths per GPU stream from HBM",
                    "parallelism": f"{world} x independent chain shards, one NCCL all-reduce of the block vector per step"},
@@ -339,6 +339,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="C3", choices=["C3", "C2", "C5"],
                     help="C3: the metric's configuration (N=256, worm on), weak scaling; C5: 4096 N=64 chains split over the GPUs")
+    ap.add_argument("--rng", default="philox", choices=["philox", "mt"],
+                    help="philox: the production streams; mt: every chain replays its own MT19937 stream in the reference's order")
     ap.add_argument("--schedule", type=int, default=-1, help="-1 auto, 0 one warp per chain, 1 team (4 warps per chain)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -406,6 +406,7 @@ __device__ inline void mt_seed(unsigned* mt, int& mti, unsigned seed) {
     for (int i = 1; i < 624; ++i) mt[i] = 69069u * mt[i - 1];
     mti = 624;
 }
+__device__ __forceinline__ unsigned mt_temper(unsigned y);
 static __device__ __noinline__ unsigned mt_next(unsigned* mt, int* pmti) {
     int mti = *pmti;
     if (mti >= 624) {
@@ -418,24 +419,35 @@ static __device__ __noinline__ unsigned mt_next(unsigned* mt, int* pmti) {
     }
     unsigned y = mt[mti++];
     *pmti = mti;
+    return mt_temper(y);
+}
+__device__ __forceinline__ double mt_grnd(GS* gs) {                 // [0,1] inclusive
+    return (double)mt_next(gs->mt, &gs->mti) / 4294967295.0;
+}
+// one attempt of the polar method (random_mod.f90:195-219): two draws in, accepted iff w <= 1, first deviate out
+__device__ __forceinline__ bool mt_polar(unsigned r1, unsigned r2, double& g) {
+    const double u1 = 2.0 * ((double)r1 / 4294967295.0) - 1.0;
+    const double u2 = 2.0 * ((double)r2 / 4294967295.0) - 1.0;
+    const double w = u1 * u1 + u2 * u2;
+    if (!(w <= 1.0)) return false;
+    g = u1 * sqrt((-2.0 * log(w)) / w);
+    return true;
+}
+static __device__ __noinline__ double mt_rangauss(GS* gs) {
+    double g;
+    unsigned r1, r2;
+    do {
+        r1 = mt_next(gs->mt, &gs->mti);
+        r2 = mt_next(gs->mt, &gs->mti);
+    } while (!mt_polar(r1, r2, g));
+    return g;
+}
+__device__ __forceinline__ unsigned mt_temper(unsigned y) {
     y ^= (y >> 11);
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
     y ^= (y >> 18);
     return y;
-}
-__device__ __forceinline__ double mt_grnd(GS* gs) {                 // [0,1] inclusive
-    return (double)mt_next(gs->mt, &gs->mti) / 4294967295.0;
-}
-static __device__ __noinline__ double mt_rangauss(GS* gs) {                // random_mod.f90:195-219, first deviate
-    double u1, u2, w;
-    do {
-        u1 = 2.0 * mt_grnd(gs) - 1.0;
-        u2 = 2.0 * mt_grnd(gs) - 1.0;
-        w = u1 * u1 + u2 * u2;
-    } while (!(w <= 1.0));
-    w = sqrt((-2.0 * log(w)) / w);
-    return u1 * w;
 }
 
 // Philox4x32-10 (Salmon et al., SC'11); counter = (ctr_lo, ctr_hi, chain, tag), key = seed
@@ -489,12 +501,59 @@ __device__ __forceinline__ void rng_gauss_fill(GS* gs, RngS* pst, int dim, int b
     const int n = nb * dim;
     double* dst = seg_new(gs);
     if (MT) {
+#ifdef PIGS_MT_SERIAL_GAUSS
         if (G.tid == 0) {
             for (int i = 0; i < n; ++i) {
                 int j = i / dim, k = i - j * dim;
                 dst[k * cP.S + b0 + j * bstride] = mt_rangauss(gs);
             }
         }
+#else
+        // The reference draws the n deviates one after the other; every attempt of the polar method consumes exactly
+        // two words of the stream whether it is accepted or not, so attempt a reads words mti + 2a, mti + 2a + 1 of
+        // the state block and the i-th deviate is the i-th ACCEPTED attempt: the lanes of the first warp run 32
+        // attempts at once (tempering, log, sqrt in parallel), a ballot ranks the accepted ones, and the stream
+        // position moves past the attempt that delivered the n-th deviate -- the same words consumed, the same
+        // deviates, the same MT19937 state as the serial loop.  The attempt that triggers or straddles the refill
+        // of the 624-word block goes through the serial code.
+        int produced = 0;
+        while (produced < n) {                                  // group-uniform
+            const int mti = gs->mti;
+            const int avail = (624 - mti) >> 1;                 // whole attempts left in this block (<= 0: refill first)
+            if (avail <= 0) {
+                if (G.tid == 0) {
+                    const unsigned r1 = mt_next(gs->mt, &gs->mti), r2 = mt_next(gs->mt, &gs->mti);
+                    double gv;
+                    const bool ok = mt_polar(r1, r2, gv);
+                    if (ok) { const int j = produced / dim, k = produced - j * dim; dst[k * cP.S + b0 + j * bstride] = gv; }
+                    gs->bc[7] = ok ? 1.0 : 0.0;
+                }
+                gsync(gs);
+                produced += (int)gs->bc[7];
+                gsync(gs);
+                continue;
+            }
+            if (G.warp == 0) {
+                const int A = avail < 32 ? avail : 32;
+                bool ok = false;
+                double gv = 0.0;
+                if (G.lane < A) ok = mt_polar(mt_temper(gs->mt[mti + 2 * G.lane]), mt_temper(gs->mt[mti + 2 * G.lane + 1]), gv);
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                const int need = n - produced, tot = __popc(m);
+                const int take = tot < need ? tot : need;
+                const int used = tot < need ? A : (int)__fns(m, 0, need) + 1;     // attempts consumed
+                const int rank = __popc(m & ((1u << G.lane) - 1u));
+                if (ok && rank < take) {
+                    const int i = produced + rank, j = i / dim, k = i - j * dim;
+                    dst[k * cP.S + b0 + j * bstride] = gv;
+                }
+                if (G.lane == 0) { gs->mti = mti + 2 * used; gs->bc[7] = (double)take; }
+            }
+            gsync(gs);
+            produced += (int)gs->bc[7];
+            gsync(gs);
+        }
+#endif
     } else {
         unsigned long long ctr = pst->ctr;
         for (int i = G.tid; i < n; i += G.size) {
