@@ -728,7 +728,7 @@ static __device__ __noinline__ void LocalEnergy(GS* gs, const double* Rx, double
     const Grp G = grp(gs);
     const double* Ry = Rx + PY;
     const double* Rz = Rx + PZ;
-    const double* tV = gs->tabV;
+    const double* tV = gs->tabV;  (void)tV;
     const double* tW = gs->tabW;
     double s[4] = {0.0, 0.0, 0.0, 0.0};      // sum |F_i|^2, pair lap (x2), pair pot (x2), one-body pot
     double oneLap = 0.0;
@@ -785,7 +785,7 @@ static __device__ __forceinline__ void ThermEnergy(GS* gs, double* out) {      /
     const Grp G = grp(gs);
     const int nitem = 2 * cP.Nb * cP.Np;
     const double dt = cP.dt;
-    const double* tV = gs->tabV;
+    const double* tV = gs->tabV;  (void)tV;
     double s[2] = {0.0, 0.0};       // E sum, Ep
     for (int it = G.tid; it < nitem; it += G.size) {
         int ib = it / cP.Np, i = it - ib * cP.Np;
