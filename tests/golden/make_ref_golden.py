@@ -35,7 +35,9 @@ def main():
     G["stream"] = dict(cfg=oracle_cfg(CW), seed=1982, grnd=[r.grnd().hex() for _ in range(1300)],
                        rangauss=[r.rangauss().hex() for _ in range(300)])
     for name, cfg, Nblock, Nstep in (("CW", CW, 4, 25), ("CWX", CWX, 5, 25), ("CS", CS, 3, 20), ("C1", C1, 2, 10), ("C2", C2, 2, 2),
-                                     ("CREF", CREF, 2, 3), ("C3", C3, 2, 2)):      # the shipped vpi.in; the benchmarked size
+                                     ("CREF", CREF, 2, 3), ("C3", C3, 2, 2),      # the shipped vpi.in; the benchmarked size
+                                     ("2D", dict(CWX, dim=2, density=0.3), 3, 20),      # (swapping = F walks off unallocated arrays in the reference, Q22)
+                                     ("Nlev1", dict(CWX, Nlev=1, Lstag=4), 3, 20)):
         c = oracle_cfg(cfg)
         rr = pigs_ref.Ref(c, Nblock=Nblock, Nstep=Nstep)
         G["program"].append(dict(name=name, cfg=c, Nblock=Nblock, Nstep=Nstep,
