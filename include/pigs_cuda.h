@@ -202,7 +202,11 @@ int  pigs_load_checkpoint(pigs_handle h, const char* path);
 int  pigs_move(pigs_handle h, int move, int ip, int half, int32_t* accepted, int32_t* aux);
 
 /* UpdateAction (vpi_mod.f90:2491): n independent evaluations on host data.
- * R[n][Np][dim] slices, ip[n], ib[n], xnew[n][dim], xold[n][dim] -> DeltaS[n] */
+ * R[n][Np][dim] slices, ip[n], ib[n], xnew[n][dim], xold[n][dim] -> DeltaS[n].
+ * Evaluated with the reference's own roundings of the minimum image and of rij2 (pbc_mod.f90:29-52), as the MT19937
+ * replay kernels do, so that partners lying exactly on the cutoff sphere (perfect crystal lattices) are decided as the
+ * reference decides them.  A handle created with table_mode = 2 explicitly runs the production (Philox) instance of
+ * the pair loop instead (shared-memory tables, fused r^2): identical except on that set of measure zero. */
 int  pigs_update_action(pigs_handle h, int n, const double* R, const int32_t* ip, const int32_t* ib,
                         const double* xnew, const double* xold, double* DeltaS);
 /* LocalEnergy (sample_mod.f90:154): R[n][Np][dim] -> E[n],Kin[n],Pot[n] */

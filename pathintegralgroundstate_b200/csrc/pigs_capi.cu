@@ -958,7 +958,9 @@ extern "C" int pigs_update_action(pigs_handle h, int n, const double* R, const i
     { std::lock_guard<std::mutex> lk(g_launch_mutex);
     int rc = guard_enter(h);
     if (rc) return rc;
-    CK(launch_update_action(P.trap, h->var == 2, P, n, (const double*)dR.p, (const int*)dip.p, (const int*)dib.p, (const double*)dxn.p,
+    // default: global-memory tables and the reference's roundings; a handle created with table_mode = 2 EXPLICITLY runs the
+    // production (Philox) instance of the pair loop instead -- shared-memory tables, fused r^2, rint minimum image
+    CK(launch_update_action(P.trap, h->hp.table_mode == 2, P, n, (const double*)dR.p, (const int*)dip.p, (const int*)dib.p, (const double*)dxn.p,
                             (const double*)dxo.p, (double*)dS.p, h->st));
     rc = guard_leave(h);
     if (rc) return rc; }

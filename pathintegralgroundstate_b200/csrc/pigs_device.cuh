@@ -345,6 +345,27 @@ __device__ __forceinline__ double mimg_lt_first(double d, double L, double Lh) {
 // could be a constant-bank operand of the FMA instead of an LDC per iteration is not expressible: ptxas folds any
 // materialisation of the constant back into an immediate.)
 __device__ __forceinline__ double magic52() { return 6755399441055744.0; }
+// XR ("reference rounding") instances of the pair loop -- the MT19937 replay kernels and the unit entry, i.e. wherever
+// the results must be the reference's own -- take the reference's decisions bit for bit; the Philox production kernel
+// keeps the faster forms (measured: the exact forms cost 3.6 % at C3, 6.5 % at C2), which sample the same distribution:
+// the two differ on a set of measure zero.
+// The reference's decision, d > L/2 / d < -L/2 on the separation itself, as two compares and one FMA: the same three
+// FP64 slots as the 2^52 form.  It differs from d - L*rint(d/L) only when |d| sits within an ulp or two of L/2, where
+// the rounded product d*(1/L) and the comparison can disagree; both images then have the same |d| to an ulp, but a
+// pair that lies EXACTLY on the cutoff sphere (rcut = L/2 along the shortest box edge, zero transverse separation:
+// the aligned neighbours of a perfect crystal lattice, BASELINE configs[3] started from config_ini.in) is inside
+// the cutoff for one image and outside for the other, and its force component changes sign.
+__device__ __forceinline__ double mimg_cmp(double d, double L, double Lh) {
+    const int qhi = (d > Lh) ? 0x3ff00000 : ((d < -Lh) ? (int)0xbff00000 : 0);
+    return fma(-__hiloint2double(qhi, 0), L, d);
+}
+// rij2 exactly as MinimumImage accumulates it (pbc_mod.f90:29-52): three rounded products, added in order.  With
+// fused multiply-adds the sum can land one ulp away, which matters for one thing only: a partner that lies on the
+// cutoff sphere to the last bit -- a whole neighbour shell of a perfect hcp lattice does (BASELINE configs[3] from
+// config_ini.in: six neighbours at r = rcut exactly) -- is inside for one rounding and outside for the other.
+__device__ __forceinline__ double r2_ref(double d0, double d1, double d2) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+}
 __device__ __forceinline__ double mimg_fast(double d, double L, double invL) {
 #if defined(PIGS_MIMG_FRND)
     // FRND.F64 on the conversion pipe: 2 FP64 slots instead of 3 and no magic constant (-12 FP64 instructions per
@@ -355,6 +376,11 @@ __device__ __forceinline__ double mimg_fast(double d, double L, double invL) {
     const double MAGIC = magic52();
     double q = fma(d, invL, MAGIC) - MAGIC;
     return fma(-q, L, d);
+}
+
+// the minimum image of the pair loops: component k (a literal at every call site)
+__device__ __forceinline__ double mimg_hot(double d, int k, double invL) {
+    return mimg_fast(d, cP.L[k], invL);
 }
 
 // ------------------------------------------------------------------ warp reductions
@@ -589,9 +615,9 @@ __device__ __forceinline__ PairGeom pair_geom(bool valid, double x0, double x1, 
     PairGeom g;
     g.d0 = x0 - rx; g.d1 = x1 - ry; g.d2 = x2 - rz;
     if (!TRAP) {
-        g.d0 = mimg_fast(g.d0, cP.L[0], cP.invL[0]);
-        g.d1 = mimg_fast(g.d1, cP.L[1], cP.invL[1]);
-        g.d2 = mimg_fast(g.d2, cP.L[2], cP.invL[2]);
+        g.d0 = mimg_hot(g.d0, 0, cP.invL[0]);
+        g.d1 = mimg_hot(g.d1, 1, cP.invL[1]);
+        g.d2 = mimg_hot(g.d2, 2, cP.invL[2]);
     }
     double r2 = g.d0 * g.d0 + g.d1 * g.d1 + g.d2 * g.d2;
     // PBC: both positions cut at rcut (Q24).  Trap: UpdatePot cuts only the OLD
@@ -787,21 +813,21 @@ __device__ __forceinline__ void rsqrt_sqrt_q(double x, double& ir, double& r) {
     ir = fma(0.5 * y, e, y);
     r = fma(0.5 * r0, e, r0);
 }
-template <bool NEED_IR, bool WRAPPED = false>
+template <bool NEED_IR, bool WRAPPED = false, bool XR = false>
 __device__ __forceinline__ Pos2 pos_geom(double d0, double d1, double d2, const LoopK* K = nullptr) {
     Pos2 g;
     const double inv_dr = K ? K->idr : cP.inv_dr;
     if (WRAPPED) {                   // the components are minimum-image components already
         g.d0 = d0; g.d1 = d1; g.d2 = d2;
+    } else if (XR) {
+        g.d0 = mimg_cmp(d0, cP.L[0], cP.Lh[0]); g.d1 = mimg_cmp(d1, cP.L[1], cP.Lh[1]); g.d2 = mimg_cmp(d2, cP.L[2], cP.Lh[2]);
     } else if (PIGS_LOOPV & 4) {
         g.d0 = mimg_hi(d0, cP.L[0], cP.LhF[0]); g.d1 = mimg_hi(d1, cP.L[1], cP.LhF[1]); g.d2 = mimg_hi(d2, cP.L[2], cP.LhF[2]);
     } else {
-        {
-        g.d0 = mimg_fast(d0, cP.L[0], K ? K->iL0 : cP.invL[0]); g.d1 = mimg_fast(d1, cP.L[1], K ? K->iL1 : cP.invL[1]);
-        g.d2 = mimg_fast(d2, cP.L[2], K ? K->iL2 : cP.invL[2]);
-        }
+        g.d0 = mimg_hot(d0, 0, K ? K->iL0 : cP.invL[0]); g.d1 = mimg_hot(d1, 1, K ? K->iL1 : cP.invL[1]);
+        g.d2 = mimg_hot(d2, 2, K ? K->iL2 : cP.invL[2]);
     }
-    const double r2 = g.d0 * g.d0 + g.d1 * g.d1 + g.d2 * g.d2;
+    const double r2 = XR ? r2_ref(g.d0, g.d1, g.d2) : g.d0 * g.d0 + g.d1 * g.d1 + g.d2 * g.d2;
     if (PIGS_LOOPV & 32) {
         // the cutoff acts on the table INDEX, off the critical path: sqrt of the unclamped r^2 (finite: the self
         // partner is poisoned with 1e150, not infinity), then i0 = zero tail unless r^2 <= rcut^2 (Q24)
@@ -851,13 +877,13 @@ __device__ __forceinline__ void lk2_val_d1(const Lk& k, unsigned sb, double& v, 
     lk_val_d1<SM, WHICH, VF>(k, v, d1);
 }
 // both positions of the displaced bead against ONE partner; dn/dq = x_new - r_j, x_old - r_j before the minimum image
-template <bool VSM, bool WSM, bool WRAPPED = false>
+template <bool VSM, bool WSM, bool WRAPPED = false, bool XR = false>
 __device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW, double dn0, double dn1, double dn2, double dq0,
                                            double dq1, double dq2, double& pot, double& psi, double (&fn)[3], double (&fo)[3],
                                            const LoopK* K = nullptr) {
     if (kind == 1) {
         {
-            const Pos2 g = pos_geom<true, WRAPPED>(dn0, dn1, dn2, K);
+            const Pos2 g = pos_geom<true, WRAPPED, XR>(dn0, dn1, dn2, K);
             double v, dv;
             lk2_val_d1<VSM, 0, VSM>(g.k, sbV, v, dv);
             pot += v;
@@ -865,7 +891,7 @@ __device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW,
             fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
         }
         {
-            const Pos2 g = pos_geom<true, WRAPPED>(dq0, dq1, dq2, K);
+            const Pos2 g = pos_geom<true, WRAPPED, XR>(dq0, dq1, dq2, K);
             double v, dv;
             lk2_val_d1<VSM, 0, VSM>(g.k, sbV, v, dv);
             pot -= v;
@@ -873,8 +899,8 @@ __device__ __forceinline__ void pair_body2(int kind, unsigned sbV, unsigned sbW,
             fo[0] += s * g.d0; fo[1] += s * g.d1; fo[2] += s * g.d2;
         }
     } else {
-        const Pos2 gn = pos_geom<false, WRAPPED>(dn0, dn1, dn2, K);
-        const Pos2 go = pos_geom<false, WRAPPED>(dq0, dq1, dq2, K);
+        const Pos2 gn = pos_geom<false, WRAPPED, XR>(dn0, dn1, dn2, K);
+        const Pos2 go = pos_geom<false, WRAPPED, XR>(dq0, dq1, dq2, K);
         pot += lk2_val<VSM, 0, VSM>(gn.k, sbV) - lk2_val<VSM, 0, VSM>(go.k, sbV);
         if (kind == 2) psi += lk2_val<WSM, 1, VSM>(gn.k, sbW) - lk2_val<WSM, 1, VSM>(go.k, sbW);
     }
@@ -894,10 +920,10 @@ __device__ __forceinline__ void pair_loop3(int kind, const double* Rx, int ip0, 
     const unsigned lt = (1u << lane) - 1u;
     int qn = 0, qh = 0;
     for (int blk = 0, j = lane; blk < nblk; ++blk, j += 32) {
-        const double a0 = mimg_fast(xn[0] - cur.x, cP.L[0], cP.invL[0]), a1 = mimg_fast(xn[1] - cur.y, cP.L[1], cP.invL[1]),
-                     a2 = mimg_fast(xn[2] - cur.z, cP.L[2], cP.invL[2]);
-        const double b0 = mimg_fast(xo[0] - cur.x, cP.L[0], cP.invL[0]), b1 = mimg_fast(xo[1] - cur.y, cP.L[1], cP.invL[1]),
-                     b2 = mimg_fast(xo[2] - cur.z, cP.L[2], cP.invL[2]);
+        const double a0 = mimg_hot(xn[0] - cur.x, 0, cP.invL[0]), a1 = mimg_hot(xn[1] - cur.y, 1, cP.invL[1]),
+                     a2 = mimg_hot(xn[2] - cur.z, 2, cP.invL[2]);
+        const double b0 = mimg_hot(xo[0] - cur.x, 0, cP.invL[0]), b1 = mimg_hot(xo[1] - cur.y, 1, cP.invL[1]),
+                     b2 = mimg_hot(xo[2] - cur.z, 2, cP.invL[2]);
         p += 96;
         if (blk + 1 < nblk) { cur.x = ldpath(p); cur.y = ldpath(p + PY); cur.z = ldpath(p + PZ); }      // in place, one block ahead
         const double r2n = a0 * a0 + a1 * a1 + a2 * a2, r2o = b0 * b0 + b1 * b1 + b2 * b2;
@@ -934,7 +960,7 @@ struct Carry {
     const double* next;
     const LoopK* K;
 };
-template <bool VSM, bool WSM>
+template <bool VSM, bool WSM, bool XR = false>
 __device__ __forceinline__ void pair_loop2(int kind, const double* Rx, int ip0, int j0, int jstride, const double (&xo)[3],
                                            const double (&xn)[3], Partner cur, double& pot, double& psi, double (&fn)[3],
                                            double (&fo)[3], Carry* cy = nullptr) {
@@ -959,7 +985,7 @@ __device__ __forceinline__ void pair_loop2(int kind, const double* Rx, int ip0, 
             p += pstep;
             if (left > jstride) { a.x = ldpath(p); a.y = ldpath(p + PY); a.z = ldpath(p + PZ); }
             else if (pn) { a.x = ldpath(pn); a.y = ldpath(pn + PY); a.z = ldpath(pn + PZ); }
-            pair_body2<VSM, WSM>(kind, sbV, sbW, dn0, dn1, dn2, dq0, dq1, dq2, pot, psi, fn, fo, cy->K);
+            pair_body2<VSM, WSM, false, XR>(kind, sbV, sbW, dn0, dn1, dn2, dq0, dq1, dq2, pot, psi, fn, fo, cy->K);
         }
         cy->a = a;
         return;
@@ -988,8 +1014,8 @@ __device__ __forceinline__ void pair_loop2(int kind, const double* Rx, int ip0, 
                 a.x = ldpath(pn); a.y = ldpath(pn + PY); a.z = ldpath(pn + PZ);
                 if (left0 > jstride) { b.x = ldpath(pn + pstep); b.y = ldpath(pn + pstep + PY); b.z = ldpath(pn + pstep + PZ); }
             }
-            pair_body2<VSM, WSM>(kind, sbV, sbW, an0, an1, an2, aq0, aq1, aq2, pot, psi, fn, fo);
-            pair_body2<VSM, WSM>(kind, sbV, sbW, bn0, bn1, bn2, bq0, bq1, bq2, pot, psi, fn, fo);
+            pair_body2<VSM, WSM, false, XR>(kind, sbV, sbW, an0, an1, an2, aq0, aq1, aq2, pot, psi, fn, fo);
+            pair_body2<VSM, WSM, false, XR>(kind, sbV, sbW, bn0, bn1, bn2, bq0, bq1, bq2, pot, psi, fn, fo);
         }
         cy->a = a; cy->b = b;
         return;
@@ -1008,7 +1034,7 @@ PIGS_PRAGMA_UNROLL
             if (PIGS_LOOPV & (64 | 128)) { cur.x = ldpath_ca(p); cur.y = ldpath_ca(p + PY); cur.z = ldpath_ca(p + PZ); }
             else { cur.x = ldpath(p); cur.y = ldpath(p + PY); cur.z = ldpath(p + PZ); }      // in place, one iteration ahead
         }
-        pair_body2<VSM, WSM>(kind, sbV, sbW, dn0, dn1, dn2, dq0, dq1, dq2, pot, psi, fn, fo);
+        pair_body2<VSM, WSM, false, XR>(kind, sbV, sbW, dn0, dn1, dn2, dq0, dq1, dq2, pot, psi, fn, fo);
     }
 }
 
@@ -1030,7 +1056,7 @@ __device__ __forceinline__ double assemble_dS(int ib, const double (&v)[8]) {
 //                   combination with other warps (returns 0).
 // The lane with add_self adds the one-body (trap) terms once.  `first` holds the
 // coordinates of partner j0 (preloaded by the caller; unused lanes pass anything).
-template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
+template <bool TRAP, bool VSM, bool WSM, bool VPAIR, bool XR = false>
 __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, int j0, int jstride, bool add_self,
                                             const double (&xo)[3], const double (&xn)[3], int lane, double* part,
                                             const Partner& first, double* lin = nullptr, Carry* cy = nullptr,
@@ -1053,7 +1079,7 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
         }
     }
     if ((PIGS_LOOPV & 512) && !TRAP && !VPAIR && ring) pair_loop3<VSM, WSM>(kind, Rx, ip0, lane, xo, xn, first, ring, pot, psi, fn, fo);
-    else if (PIGS_LOOPV != 0 && !TRAP && !VPAIR) pair_loop2<VSM, WSM>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo, cy);
+    else if (PIGS_LOOPV != 0 && !TRAP && !VPAIR) pair_loop2<VSM, WSM, XR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo, cy);
     else pair_loop<TRAP, VSM, WSM, VPAIR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
     if (lin) {
         if (kind == 0) { *lin = cP.wS[ib & 1] * pot; return 0.0; }

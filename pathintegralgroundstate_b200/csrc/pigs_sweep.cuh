@@ -62,7 +62,7 @@ __device__ __forceinline__ int div_dim(int i) {          // i / cP.dim for dim i
 // Work split: with at least as many beads as warps each warp takes whole beads
 // (split = 1) and reduces to DeltaS with shuffles only; with fewer beads the
 // partners of a bead are divided over `split` warps and combined through smem.
-template <int VAR>
+template <int VAR, bool XR>
 static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, int bstride, int nb, double wfirst,
                                                       double wlast, bool roll) {
     const Grp G = grp(gs);
@@ -110,7 +110,7 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
             else if (m + 1 < nb && have) first = load_partner(Rx + sstride, lane);
             if (roll && lane == 0 && m + cA.pfdist < nb) prefetch_slice_L2(Rx + pfoff);
             double lin;
-            const double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM, PIGS_VPAIR>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn,
+            const double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM, PIGS_VPAIR, XR>(Rx, ip0, ib, lane, 32, lane == 0, xo, xn,
                                                                                  lane, nullptr, cur, &lin, TWO ? &cy : nullptr);
             const double w = (m == 0) ? wfirst : ((m == nb - 1) ? wlast : 1.0);
             Sw += w * t;
@@ -153,7 +153,7 @@ static __device__ PIGS_EVAL_INLINE double eval_action(GS* gs, int ip0, int b0, i
             int mn = (split > 1) ? tn / split : tn, sn_ = (split > 1) ? tn - mn * split : 0;
             if (sn_ * 32 + G.lane < cP.Np) first = load_partner(slice(gs, b0 + mn * bstride), sn_ * 32 + G.lane);
         }
-        double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM, PIGS_VPAIR>(slice(gs, ib), ip0, ib, s * 32 + G.lane, 32 * split,
+        double t = bead_eval<PIGS_TRAP, PIGS_VSM, PIGS_WSM, PIGS_VPAIR, XR>(slice(gs, ib), ip0, ib, s * 32 + G.lane, 32 * split,
                                                            (s == 0) && (G.lane == 0), xo, xn, G.lane,
                                                            (split == 1) ? nullptr : part + task * 8, cur);
         if (split == 1) {
@@ -426,7 +426,7 @@ PIGS_T __device__ __forceinline__ bool run_move_body(GS* gs, ull* pctr, int flag
         phase_pre<MT, VAR>(gs, ph, b0, bs, nb, wf, wl, roll);
         const int ipp = gs->pk.ip0;
         asm volatile("" ::: "memory");
-        const double S = eval_action<VAR>(gs, ipp, b0, bs, nb, wf, wl, roll);
+        const double S = eval_action<VAR, MT>(gs, ipp, b0, bs, nb, wf, wl, roll);      // replay: the reference's own roundings
         asm volatile("" ::: "memory");
         r = phase_post<MT, VAR>(gs, ph, S);
         if (r) break;
@@ -808,10 +808,10 @@ static __device__ __forceinline__ void ThermEnergy(GS* gs, double* out) {      /
             for (int j = 0; j < cP.Np; ++j) {
                 if (j == i) continue;
                 double d0 = xi[0] - Rx[pidx(j)], d1 = xi[1] - Ry[pidx(j)], d2 = xi[2] - Rz[pidx(j)];
-                if (!PIGS_TRAP) {
-                    d0 = mimg_fast(d0, cP.L[0], cP.invL[0]); d1 = mimg_fast(d1, cP.L[1], cP.invL[1]); d2 = mimg_fast(d2, cP.L[2], cP.invL[2]);
+                if (!PIGS_TRAP) {      // the estimators take the reference's decisions bit for bit (see mimg_cmp, r2_ref)
+                    d0 = mimg_cmp(d0, cP.L[0], cP.Lh[0]); d1 = mimg_cmp(d1, cP.L[1], cP.Lh[1]); d2 = mimg_cmp(d2, cP.L[2], cP.Lh[2]);
                 }
-                double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+                double r2 = r2_ref(d0, d1, d2);
                 if (PIGS_TRAP || r2 <= cP.rcut2) {
                     double ir = rsqrt_pos(r2);
                     double r = r2 * ir;
@@ -833,10 +833,10 @@ static __device__ __forceinline__ void ThermEnergy(GS* gs, double* out) {      /
                 if (!(cP.Np & 1) && m == half && i >= half) break;
                 int j = i + m; if (j >= cP.Np) j -= cP.Np;
                 double d0 = xi[0] - Rx[pidx(j)], d1 = xi[1] - Ry[pidx(j)], d2 = xi[2] - Rz[pidx(j)];
-                if (!PIGS_TRAP) {
-                    d0 = mimg_fast(d0, cP.L[0], cP.invL[0]); d1 = mimg_fast(d1, cP.L[1], cP.invL[1]); d2 = mimg_fast(d2, cP.L[2], cP.invL[2]);
+                if (!PIGS_TRAP) {      // the estimators take the reference's decisions bit for bit (see mimg_cmp, r2_ref)
+                    d0 = mimg_cmp(d0, cP.L[0], cP.Lh[0]); d1 = mimg_cmp(d1, cP.L[1], cP.Lh[1]); d2 = mimg_cmp(d2, cP.L[2], cP.Lh[2]);
                 }
-                double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+                double r2 = r2_ref(d0, d1, d2);
                 if (PIGS_TRAP || r2 <= cP.rcut2) {
                     Lk k = lk_prep(sqrt_pos(r2));
                     if (PIGS_TRAP) k.i0 = min(k.i0, cP.Nmax - 1);

@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(128) k_update_action(int n, const double* Rsoa
         Partner first;
         first.x = first.y = first.z = 0.0;
         if (lane < cP.Np) first = load_partner(Rx, lane);
-        double t = bead_eval<TRAP, SM, SM, false>(Rx, ip[e] - 1, ib[e], lane, 32, lane == 0, xo, xn, lane, nullptr, first);
+        // global-memory tables: the reference's roundings (XR); shared-memory tables: exactly the production (Philox) instance
+        double t = bead_eval<TRAP, SM, SM, false, !SM>(Rx, ip[e] - 1, ib[e], lane, 32, lane == 0, xo, xn, lane, nullptr, first);
         if (lane == 0) dS[e] = t;
     }
 }

@@ -43,6 +43,17 @@ def main():
         G["program"].append(dict(name=name, cfg=c, Nblock=Nblock, Nstep=Nstep,
                                  e_vpi=[[x.hex() for x in row] for row in rr.file("e_vpi.out").tolist()],
                                  et_vpi=[[x.hex() for x in row] for row in rr.file("et_vpi.out").tolist()]))
+    # BASELINE configs[3]: hcp crystal, N = 180 in an orthorhombic box, started from config_ini.in (served from memory)
+    from pathintegralgroundstate_b200.workloads import config, hcp_lattice
+    c4 = dict(config("C4"), CWorm=8.0)
+    c4.pop("tables")
+    R, Lb = hcp_lattice(density=c4["density"])
+    c4["Lbox"] = [float(x) for x in Lb]
+    c = oracle_cfg(c4)
+    rr = pigs_ref.Ref(c, Nblock=2, Nstep=2, lattice=(R[:c4["Np"]], Lb))
+    G["program"].append(dict(name="C4", cfg=c, Nblock=2, Nstep=2, lattice=[[float(x).hex() for x in row] for row in R[:c4["Np"]]],
+                             e_vpi=[[x.hex() for x in row] for row in rr.file("e_vpi.out").tolist()],
+                             et_vpi=[[x.hex() for x in row] for row in rr.file("et_vpi.out").tolist()]))
     out = os.path.join(ROOT, "tests", "golden", "ref_golden.json")
     json.dump(G, open(out, "w"), indent=0)
     print("wrote", out, os.path.getsize(out), "bytes")

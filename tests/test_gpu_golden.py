@@ -23,7 +23,7 @@ def _cfg(c):
     return c
 
 
-def gpu_program(cfg, Nblock, Nstep):
+def gpu_program(cfg, Nblock, Nstep, lattice=None):
     """`program vpi` over the C ABI: tables (vpi.f90:146-153), init (vpi_mod.f90:149-259: uniform random start drawn
     from the chain's own MT19937 stream), then per block the step loop on the device and the normalisation of
     vpi.f90:477-518"""
@@ -31,8 +31,11 @@ def gpu_program(cfg, Nblock, Nstep):
     g.fill_tables("hfdb")
     dim, Np, Nb = g.dim, g.Np, int(cfg["Nb"])
     g.sgrnd(int(cfg["seed"]), chain=0)
-    u = g.grnd(Np * dim, chain=0).reshape(Np, dim)
-    R = (2.0 * np.asarray(g.geo["a_ho"][:dim]) if g.geo["trap"] else np.asarray(g.geo["Lbox"][:dim])) * (u - 0.5)
+    if lattice is not None:                                     # crystal = T: positions from config_ini.in, no draws
+        R = np.asarray(lattice, float)
+    else:
+        u = g.grnd(Np * dim, chain=0).reshape(Np, dim)
+        R = (2.0 * np.asarray(g.geo["a_ho"][:dim]) if g.geo["trap"] else np.asarray(g.geo["Lbox"][:dim])) * (u - 0.5)
     Path = np.broadcast_to(R, (2 * Nb + 1, Np, dim)).copy()
     g.set_state(0, Path, np.stack([Path[Nb, Np - 1], Path[Nb, Np - 1]]), 0, 0)
     e, et = [], []
@@ -59,11 +62,14 @@ def test_mt19937_stream_matches_reference_golden_bit_for_bit():
     assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)) < 1e-14
 
 
-@pytest.mark.parametrize("case", range(9))
+@pytest.mark.parametrize("case", range(10))
 def test_whole_program_matches_reference_golden(case):
     case = json.load(open(GOLDEN))["program"][case]
     cfg = _cfg(case["cfg"])
-    e, et = gpu_program(cfg, case["Nblock"], case["Nstep"])
+    if "Lbox_crystal" in cfg:
+        cfg["Lbox"] = cfg["Lbox_crystal"]
+    lat = [[h(x) for x in row] for row in case["lattice"]] if "lattice" in case else None
+    e, et = gpu_program(cfg, case["Nblock"], case["Nstep"], lat)
     we = np.array([[h(x) for x in row] for row in case["e_vpi"]])
     wet = np.array([[h(x) for x in row] for row in case["et_vpi"]])
     assert e.shape == we.shape and et.shape == wet.shape and e.shape[0] >= 1, case["name"]
@@ -75,3 +81,34 @@ def test_whole_program_matches_reference_golden(case):
     assert np.allclose(e[:, 3], we[:, 3], rtol=1e-9, atol=1e-9 * np.abs(we[:, 3]).max()), (case["name"], e, we)
     scale = np.abs(we[:, 2]).max()
     assert np.max(np.abs(e[:, 1:3] - we[:, 1:3])) <= 1e-7 * max(scale, 1.0), (case["name"], e, we)
+
+
+def test_update_action_on_the_perfect_lattice_takes_the_reference_decisions():
+    """The hcp lattice of BASELINE configs[3] has a whole neighbour shell at r = rcut to the last bit (six partners of
+    every particle).  Whether such a partner counts depends on how r^2 is rounded: the unit entry and the replay
+    kernels accumulate it exactly as MinimumImage does (pbc_mod.f90:29-52), so they agree with the oracle -- which is
+    bit-equal to the translated reference -- on this degenerate input too (1e-10), at every slice class."""
+    from oracle.pigs_oracle import Oracle
+    case = [c for c in json.load(open(GOLDEN))["program"] if c["name"] == "C4"][0]
+    c = case["cfg"]
+    cfg = _cfg(c)
+    cfg["Lbox"] = cfg["Lbox_crystal"]
+    R = np.array([[h(x) for x in row] for row in case["lattice"]])
+    o = Oracle(c)
+    o.fill_tables()
+    g = PigsCuda(cfg, n_chains=1, rng="mt", seed=c["seed"])
+    g.set_tables(*o.get_tables())
+    d = R[0][None, :] - R
+    L = np.asarray(g.geo["Lbox"])
+    d -= L * np.rint(d / L)
+    on_sphere = np.abs(np.sqrt((d * d).sum(axis=1)) - g.geo["rcut"]) < 1e-12
+    assert on_sphere.sum() >= 4                                  # the degenerate shell is really there
+    rng = np.random.default_rng(1)
+    n = 240
+    ip = rng.integers(1, c["Np"] + 1, n).astype(np.int32)
+    ib = rng.integers(0, 2 * c["Nb"] + 1, n).astype(np.int32)
+    xold = R[ip - 1]
+    xnew = xold + rng.normal(0, 0.05, (n, 3))
+    got = g.update_action(np.broadcast_to(R, (n,) + R.shape).copy(), ip, ib, xnew, xold)
+    want = np.array([o.update_action(int(a), int(b), xn, xo, R=R) for a, b, xn, xo in zip(ip, ib, xnew, xold)])
+    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)) < 1e-10

@@ -188,11 +188,17 @@ def test_moves_bit_equal(name, cfg):
 
 
 # ------------------------------------------------------------------ the whole program
-def oracle_program(c, Nblock, Nstep):
+def oracle_program(c, Nblock, Nstep, lattice=None):
     """what `program vpi` writes to e_vpi.out / et_vpi.out, from the oracle's block sums (vpi.f90:477-518)"""
     o = po.Oracle(c)
     o.fill_tables()
-    o.init()
+    if lattice is None:
+        o.init()
+    else:                                                       # crystal = T: positions from config_ini.in (vpi_mod.f90:218-228)
+        R = np.asarray(lattice, float)
+        P = np.broadcast_to(R, (2 * c["Nb"] + 1,) + R.shape).copy()
+        o.set_state(P, np.stack([P[c["Nb"], -1]] * 2), 0, 0)
+        o.sgrnd(c["seed"])
     Np = c["Np"]
     e, et, nr, events = [], [], None, dict(open=0, close=0, swap=0)
     for ib in range(1, Nblock + 1):
@@ -256,7 +262,8 @@ def test_oracle_matches_reference_goldens():
         assert got == want or (math.isnan(got) and math.isnan(want)), case
     for case in G["program"]:
         c = case["cfg"]
-        e, et, _, _ = oracle_program(c, case["Nblock"], case["Nstep"])
+        lat = [[h(x) for x in row] for row in case["lattice"]] if "lattice" in case else None
+        e, et, _, _ = oracle_program(c, case["Nblock"], case["Nstep"], lat)
         assert [[x.hex() for x in row] for row in e.tolist()] == case["e_vpi"], case["name"]
         assert [[x.hex() for x in row] for row in et.tolist()] == case["et_vpi"], case["name"]
     o = po.Oracle(G["stream"]["cfg"])
