@@ -54,6 +54,18 @@ def main():
     G["program"].append(dict(name="C4", cfg=c, Nblock=2, Nstep=2, lattice=[[float(x).hex() for x in row] for row in R[:c4["Np"]]],
                              e_vpi=[[x.hex() for x in row] for row in rr.file("e_vpi.out").tolist()],
                              et_vpi=[[x.hex() for x in row] for row in rr.file("et_vpi.out").tolist()]))
+    # a simple-cubic lattice in a cubic box (crystal = T): neighbours at separations of EXACTLY L/2 along every axis,
+    # r = rcut to the last bit -- the minimum-image comparison and the cutoff decide on equality here
+    sc = dict(C2, Np=64, crystal=True, CWorm=0.5, Nobdm=4, Nstag=2)
+    Lc = (64 / sc["density"]) ** (1.0 / 3.0)
+    gpts = (np.arange(4) + 0.5) * (Lc / 4) - Lc / 2
+    Rsc = np.array([[x, y, z] for x in gpts for y in gpts for z in gpts])
+    sc["Lbox"] = [Lc, Lc, Lc]
+    c = oracle_cfg(sc)
+    rr = pigs_ref.Ref(c, Nblock=2, Nstep=3, lattice=(Rsc, np.array([Lc, Lc, Lc])))
+    G["program"].append(dict(name="SC64", cfg=c, Nblock=2, Nstep=3, lattice=[[float(x).hex() for x in row] for row in Rsc],
+                             e_vpi=[[x.hex() for x in row] for row in rr.file("e_vpi.out").tolist()],
+                             et_vpi=[[x.hex() for x in row] for row in rr.file("et_vpi.out").tolist()]))
     out = os.path.join(ROOT, "tests", "golden", "ref_golden.json")
     json.dump(G, open(out, "w"), indent=0)
     print("wrote", out, os.path.getsize(out), "bytes")
