@@ -66,6 +66,18 @@ def main():
     G["program"].append(dict(name="SC64", cfg=c, Nblock=2, Nstep=3, lattice=[[float(x).hex() for x in row] for row in Rsc],
                              e_vpi=[[x.hex() for x in row] for row in rr.file("e_vpi.out").tolist()],
                              et_vpi=[[x.hex() for x in row] for row in rr.file("et_vpi.out").tolist()]))
+    # the same lattice with the staging flavour of every move, and a square lattice in two dimensions
+    for name, base, npts, dim_ in (("SC64sta", dict(sc, sampling="sta", Lstag=6), 4, 3),
+                                   ("SQ36", dict(C2, dim=2, Np=36, density=0.3, crystal=True, CWorm=0.5, Nobdm=4, Nstag=2, Nk=8), 6, 2)):
+        Lq = (base["Np"] / base["density"]) ** (1.0 / dim_)
+        gq = (np.arange(npts) + 0.5) * (Lq / npts) - Lq / 2
+        Rq = np.array(np.meshgrid(*([gq] * dim_), indexing="ij")).reshape(dim_, -1).T.copy()
+        base["Lbox"] = [Lq] * dim_
+        c = oracle_cfg(base)
+        rr = pigs_ref.Ref(c, Nblock=2, Nstep=3, lattice=(Rq, np.array([Lq] * dim_)))
+        G["program"].append(dict(name=name, cfg=c, Nblock=2, Nstep=3, lattice=[[float(x).hex() for x in row] for row in Rq],
+                                 e_vpi=[[x.hex() for x in row] for row in rr.file("e_vpi.out").tolist()],
+                                 et_vpi=[[x.hex() for x in row] for row in rr.file("et_vpi.out").tolist()]))
     out = os.path.join(ROOT, "tests", "golden", "ref_golden.json")
     json.dump(G, open(out, "w"), indent=0)
     print("wrote", out, os.path.getsize(out), "bytes")
