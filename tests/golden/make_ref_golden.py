@@ -37,7 +37,8 @@ def main():
     for name, cfg, Nblock, Nstep in (("CW", CW, 4, 25), ("CWX", CWX, 5, 25), ("CS", CS, 3, 20), ("C1", C1, 2, 10), ("C2", C2, 2, 2),
                                      ("CREF", CREF, 2, 3), ("C3", C3, 2, 2),      # the shipped vpi.in; the benchmarked size
                                      ("2D", dict(CWX, dim=2, density=0.3), 3, 20),      # (swapping = F walks off unallocated arrays in the reference, Q22)
-                                     ("Nlev1", dict(CWX, Nlev=1, Lstag=4), 3, 20)):
+                                     ("Nlev1", dict(CWX, Nlev=1, Lstag=4), 3, 20),
+                                     ("CREFlong", CREF, 3, 12), ("C2worm", dict(C2, CWorm=0.5, Nobdm=5), 2, 15)):    # longer runs at N = 64
         c = oracle_cfg(cfg)
         rr = pigs_ref.Ref(c, Nblock=Nblock, Nstep=Nstep)
         G["program"].append(dict(name=name, cfg=c, Nblock=Nblock, Nstep=Nstep,

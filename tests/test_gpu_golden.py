@@ -62,7 +62,7 @@ def test_mt19937_stream_matches_reference_golden_bit_for_bit():
     assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)) < 1e-14
 
 
-@pytest.mark.parametrize("case", range(13))
+@pytest.mark.parametrize("case", range(15))
 def test_whole_program_matches_reference_golden(case):
     case = json.load(open(GOLDEN))["program"][case]
     cfg = _cfg(case["cfg"])
