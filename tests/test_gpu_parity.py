@@ -625,9 +625,13 @@ def test_update_action_shared_memory_tables(name, cfg):
     ("one particle past a 32-lane partner block", dict(CWX, Np=33)),
     ("the longest path the kernel takes: Nb = 65, 131 slices", dict(CW, Nb=65, Lstag=20, Nlev=4)),
     ("one dimension", dict(CWX, dim=1, density=0.3, Np=12)),
+    ("OBDM with two powers of the weight (Npw = 2)", dict(CWX, Npw=2)),
+    ("no structure factor (Nk = 0)", dict(CWX, Nk=0)),
+    ("translations every third step (CMFreq = 3)", dict(CWX, CMFreq=3)),
+    ("no worm cycles (Nobdm = 0) although the worm can open", dict(CWX, Nobdm=0)),
 ])
 def test_edge_shapes_replay(name, cfg):
-    _replay_block(cfg, nchain=2, nstep=3, nblock=2)
+    _replay_block(cfg, nchain=2, nstep=6 if cfg["Np"] == 16 and cfg["Nb"] == 8 else 3, nblock=2)
 
 
 def test_refused_shapes():
