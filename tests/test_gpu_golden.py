@@ -23,11 +23,11 @@ def _cfg(c):
     return c
 
 
-def gpu_program(cfg, Nblock, Nstep, lattice=None):
+def gpu_program(cfg, Nblock, Nstep, lattice=None, **kw):
     """`program vpi` over the C ABI: tables (vpi.f90:146-153), init (vpi_mod.f90:149-259: uniform random start drawn
     from the chain's own MT19937 stream), then per block the step loop on the device and the normalisation of
     vpi.f90:477-518"""
-    g = PigsCuda(cfg, n_chains=1, rng="mt", seed=cfg["seed"])
+    g = PigsCuda(cfg, n_chains=1, rng="mt", seed=cfg["seed"], **kw)
     g.fill_tables("hfdb")
     dim, Np, Nb = g.dim, g.Np, int(cfg["Nb"])
     g.sgrnd(int(cfg["seed"]), chain=0)
@@ -62,14 +62,19 @@ def test_mt19937_stream_matches_reference_golden_bit_for_bit():
     assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)) < 1e-14
 
 
-@pytest.mark.parametrize("case", range(15))
+@pytest.mark.parametrize("case", list(range(15)) + ["C4/128", "SC64/128", "C3/128"])
 def test_whole_program_matches_reference_golden(case):
+    kw = {}
+    if isinstance(case, str):                                   # the same runs with four warps per chain (partner split)
+        name, tpc = case.split("/")
+        case = [i for i, c in enumerate(json.load(open(GOLDEN))["program"]) if c["name"] == name][0]
+        kw = dict(threads_per_chain=int(tpc))
     case = json.load(open(GOLDEN))["program"][case]
     cfg = _cfg(case["cfg"])
     if "Lbox_crystal" in cfg:
         cfg["Lbox"] = cfg["Lbox_crystal"]
     lat = [[h(x) for x in row] for row in case["lattice"]] if "lattice" in case else None
-    e, et = gpu_program(cfg, case["Nblock"], case["Nstep"], lat)
+    e, et = gpu_program(cfg, case["Nblock"], case["Nstep"], lat, **kw)
     we = np.array([[h(x) for x in row] for row in case["e_vpi"]])
     wet = np.array([[h(x) for x in row] for row in case["et_vpi"]])
     assert e.shape == we.shape and et.shape == wet.shape and e.shape[0] >= 1, case["name"]
