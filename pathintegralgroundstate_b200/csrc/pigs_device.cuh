@@ -610,16 +610,15 @@ struct PairGeom {
     Lk k;
     bool in_pot, in_wf;
 };
-template <int KIND, bool TRAP, bool IS_NEW>
+template <int KIND, bool TRAP, bool IS_NEW, bool XR = false>
 __device__ __forceinline__ PairGeom pair_geom(bool valid, double x0, double x1, double x2, double rx, double ry, double rz) {
     PairGeom g;
     g.d0 = x0 - rx; g.d1 = x1 - ry; g.d2 = x2 - rz;
     if (!TRAP) {
-        g.d0 = mimg_hot(g.d0, 0, cP.invL[0]);
-        g.d1 = mimg_hot(g.d1, 1, cP.invL[1]);
-        g.d2 = mimg_hot(g.d2, 2, cP.invL[2]);
+        if (XR) { g.d0 = mimg_cmp(g.d0, cP.L[0], cP.Lh[0]); g.d1 = mimg_cmp(g.d1, cP.L[1], cP.Lh[1]); g.d2 = mimg_cmp(g.d2, cP.L[2], cP.Lh[2]); }
+        else { g.d0 = mimg_hot(g.d0, 0, cP.invL[0]); g.d1 = mimg_hot(g.d1, 1, cP.invL[1]); g.d2 = mimg_hot(g.d2, 2, cP.invL[2]); }
     }
-    double r2 = g.d0 * g.d0 + g.d1 * g.d1 + g.d2 * g.d2;
+    double r2 = XR ? r2_ref(g.d0, g.d1, g.d2) : g.d0 * g.d0 + g.d1 * g.d1 + g.d2 * g.d2;
     // PBC: both positions cut at rcut (Q24).  Trap: UpdatePot cuts only the OLD
     // position (Q12), UpdateWf cuts nothing.
     g.in_pot = valid && (TRAP ? (IS_NEW || r2 <= cP.rcut2) : (r2 <= cP.rcut2));
@@ -666,13 +665,13 @@ __device__ __forceinline__ Partner load_partner(const double* Rx, int j) {
 }
 
 // both positions of the displaced bead against ONE partner (round-1 form; pair_body2 below is the production one)
-template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
+template <bool TRAP, bool VSM, bool WSM, bool VPAIR, bool XR = false>
 __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& cur, const double (&xo)[3],
                                           const double (&xn)[3], double& pot, double& psi, double (&fn)[3], double (&fo)[3]) {
     constexpr bool MASK = TRAP || VPAIR;        // else: masked pairs read the zero tail of the tables
     if (kind == 1) {
         {
-            PairGeom g = pair_geom<1, TRAP, true>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z);
+            PairGeom g = pair_geom<1, TRAP, true, XR>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z);
             double v, dv;
             if (VPAIR) lk_val_d1_pair(g.k, v, dv); else lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
             pot += (!MASK || g.in_pot) ? v : 0.0;
@@ -680,7 +679,7 @@ __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& c
             fn[0] += s * g.d0; fn[1] += s * g.d1; fn[2] += s * g.d2;
         }
         {
-            PairGeom g = pair_geom<1, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z);
+            PairGeom g = pair_geom<1, TRAP, false, XR>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z);
             double v, dv;
             if (VPAIR) lk_val_d1_pair(g.k, v, dv); else lk_val_d1<VSM, 0, VSM>(g.k, v, dv);
             pot -= (!MASK || g.in_pot) ? v : 0.0;
@@ -689,10 +688,10 @@ __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& c
         }
     } else {
         // even and end slices share the geometry (in trap mode the end slice has no Jastrow cutoff)
-        PairGeom gn = (TRAP && kind == 2) ? pair_geom<2, TRAP, true>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z)
-                                          : pair_geom<0, TRAP, true>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z);
-        PairGeom go = (TRAP && kind == 2) ? pair_geom<2, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z)
-                                          : pair_geom<0, TRAP, false>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z);
+        PairGeom gn = (TRAP && kind == 2) ? pair_geom<2, TRAP, true, XR>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z)
+                                          : pair_geom<0, TRAP, true, XR>(valid, xn[0], xn[1], xn[2], cur.x, cur.y, cur.z);
+        PairGeom go = (TRAP && kind == 2) ? pair_geom<2, TRAP, false, XR>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z)
+                                          : pair_geom<0, TRAP, false, XR>(valid, xo[0], xo[1], xo[2], cur.x, cur.y, cur.z);
         double vn = VPAIR ? lk_val_pair(gn.k) : lk_val<VSM, 0, VSM>(gn.k);
         double vo = VPAIR ? lk_val_pair(go.k) : lk_val<VSM, 0, VSM>(go.k);
         pot += ((!MASK || gn.in_pot) ? vn : 0.0) - ((!MASK || go.in_pot) ? vo : 0.0);
@@ -714,7 +713,7 @@ __device__ __forceinline__ void pair_body(int kind, bool valid, const Partner& c
 // B200: a two-deep pipeline, an A/B ping-pong body and a 2x unrolled body were
 // all 5-25% slower -- larger loop bodies lose more than the extra latency
 // tolerance gains.)
-template <bool TRAP, bool VSM, bool WSM, bool VPAIR>
+template <bool TRAP, bool VSM, bool WSM, bool VPAIR, bool XR = false>
 __device__ __forceinline__ void pair_loop(int kind, const double* Rx, int ip0, int j0, int jstride, const double (&xo)[3],
                                           const double (&xn)[3], Partner nxt, double& pot, double& psi, double (&fn)[3],
                                           double (&fo)[3]) {
@@ -728,7 +727,7 @@ PIGS_PRAGMA_UNROLL
         const Partner cur = nxt;
         p += pstep;
         if (left > jstride) { nxt.x = ldpath(p); nxt.y = ldpath(p + PY); nxt.z = ldpath(p + PZ); }
-        pair_body<TRAP, VSM, WSM, VPAIR>(kind, left != self_left, cur, xo, xn, pot, psi, fn, fo);
+        pair_body<TRAP, VSM, WSM, VPAIR, XR>(kind, left != self_left, cur, xo, xn, pot, psi, fn, fo);
     }
 }
 
@@ -1080,7 +1079,7 @@ __device__ __forceinline__ double bead_eval(const double* Rx, int ip0, int ib, i
     }
     if ((PIGS_LOOPV & 512) && !TRAP && !VPAIR && ring) pair_loop3<VSM, WSM>(kind, Rx, ip0, lane, xo, xn, first, ring, pot, psi, fn, fo);
     else if (PIGS_LOOPV != 0 && !TRAP && !VPAIR) pair_loop2<VSM, WSM, XR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo, cy);
-    else pair_loop<TRAP, VSM, WSM, VPAIR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
+    else pair_loop<TRAP, VSM, WSM, VPAIR, XR>(kind, Rx, ip0, j0, jstride, xo, xn, first, pot, psi, fn, fo);
     if (lin) {
         if (kind == 0) { *lin = cP.wS[ib & 1] * pot; return 0.0; }
         if (kind == 2) { *lin = fma(cP.wS[2], pot, -psi); return 0.0; }
