@@ -117,3 +117,27 @@ def test_update_action_on_the_perfect_lattice_takes_the_reference_decisions():
     got = g.update_action(np.broadcast_to(R, (n,) + R.shape).copy(), ip, ib, xnew, xold)
     want = np.array([o.update_action(int(a), int(b), xn, xo, R=R) for a, b, xn, xo in zip(ip, ib, xnew, xold)])
     assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["C4", "SC64"])
+def test_estimators_on_perfect_lattices(name):
+    """g(r), the energies and S(k) on perfect lattices: separations that sit exactly on histogram-bin edges, on the
+    cutoff sphere and at L/2 -- the integer histogram must be the oracle's bit for bit, the energies agree to 1e-10"""
+    from oracle.pigs_oracle import Oracle
+    case = [c for c in json.load(open(GOLDEN))["program"] if c["name"] == name][0]
+    c = case["cfg"]
+    cfg = _cfg(c)
+    cfg["Lbox"] = cfg["Lbox_crystal"]
+    R = np.array([[h(x) for x in row] for row in case["lattice"]])
+    o = Oracle(c)
+    o.fill_tables()
+    g = PigsCuda(cfg, n_chains=1, rng="mt", seed=c["seed"])
+    g.set_tables(*o.get_tables())
+    assert np.array_equal(g.pair_correlation(R[None])[0], o.pair_correlation(R))
+    Eg, Eo = np.array([x[0] for x in g.local_energy(R[None])]), np.array(o.local_energy(R))
+    assert np.allclose(Eg, Eo, rtol=1e-10, atol=1e-10 * np.abs(Eo).max()), (Eg, Eo)
+    P = np.broadcast_to(R, (2 * c["Nb"] + 1,) + R.shape).copy()
+    Tg, To = np.array([x[0] for x in g.therm_energy(P[None])]), np.array(o.therm_energy(P))
+    assert np.allclose(Tg, To, rtol=1e-10, atol=1e-10 * np.abs(To).max()), (Tg, To)
+    Sg, So = g.structure_factor(R[None])[0], o.structure_factor(R)
+    assert np.allclose(Sg, So, rtol=1e-9, atol=1e-9 * max(np.abs(So).max(), 1.0))
