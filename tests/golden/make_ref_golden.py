@@ -38,7 +38,9 @@ def main():
                                      ("CREF", CREF, 2, 3), ("C3", C3, 2, 2),      # the shipped vpi.in; the benchmarked size
                                      ("2D", dict(CWX, dim=2, density=0.3), 3, 20),      # (swapping = F walks off unallocated arrays in the reference, Q22)
                                      ("Nlev1", dict(CWX, Nlev=1, Lstag=4), 3, 20),
-                                     ("CREFlong", CREF, 3, 12), ("C2worm", dict(C2, CWorm=0.5, Nobdm=5), 2, 15)):    # longer runs at N = 64
+                                     ("CREFlong", CREF, 3, 12), ("C2worm", dict(C2, CWorm=0.5, Nobdm=5), 2, 15),    # longer runs at N = 64
+                                     ("C1aniso", dict(C1, a_ho=[1.0, 1.3, 0.8]), 2, 10), ("trap2D", dict(C1, dim=2, a_ho=[1.0, 0.7, 1.0]), 2, 10),
+                                     ("NlevMax", dict(CWX, Nlev=4), 3, 15), ("Nstag0", dict(CWX, Nstag=0), 3, 10)):
         c = oracle_cfg(cfg)
         rr = pigs_ref.Ref(c, Nblock=Nblock, Nstep=Nstep)
         G["program"].append(dict(name=name, cfg=c, Nblock=Nblock, Nstep=Nstep,

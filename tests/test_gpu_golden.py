@@ -62,7 +62,7 @@ def test_mt19937_stream_matches_reference_golden_bit_for_bit():
     assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)) < 1e-14
 
 
-@pytest.mark.parametrize("case", list(range(15)) + ["C4/128", "SC64/128", "C3/128"])
+@pytest.mark.parametrize("case", list(range(19)) + ["C4/128", "SC64/128", "C3/128"])
 def test_whole_program_matches_reference_golden(case):
     kw = {}
     if isinstance(case, str):                                   # the same runs with four warps per chain (partner split)
