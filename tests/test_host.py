@@ -232,3 +232,30 @@ def test_cross_chain_statistics_layer():
     assert hist.tolist() == [60, 20, 0, 0, 0, 0] and contributing == 20 and mean_len == pytest.approx(1.25) and P.sum() == pytest.approx(1.0)
     cm = chain_means(sim, chains=[3, 5, 9])
     assert cm["sumE"].shape == (3,) and np.all(np.isfinite(cm["sumE"]))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/vpi.f90"), reason="needs the reference sources (build container only)")
+def test_fortran_driver_generator_applies_all_five_edits():
+    """fortran/make_vpi_cuda.py turns the reference's own vpi.f90 into the driver over the C ABI: the step loop
+    (vpi.f90:297-475) becomes ONE pigs_run_block call, everything else stays the reference's text"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "fortran", "make_vpi_cuda.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    gen = open(os.path.join(root, "fortran", "_gen", "vpi_cuda.f90")).read()
+    ref = open("/root/reference/vpi.f90").read()
+    assert gen.count("pigs_run_block(gpu,Nstep)") == 1 and gen.count("pigs_create(gpar,gpu)") == 1
+    assert "do istep=1,Nstep" not in gen and "do istep=1,Nstep" in ref
+    for needle in ("use pigs_cuda_mod", "pigs_set_tables(gpu,LogWF,VTable)", "pigs_get_block(gpu,gres,gr,Sk,gnr)",
+                   "pigs_get_state(gpu,0,Path,xend,gopen,gworm)", "pigs_get_perm(gpu,gch,giperm,gcyc,ghist,gnew,gend)",
+                   "pigs_destroy(gpu)"):
+        assert needle in gen, needle
+    # everything outside the step loop is still the reference's text: the block normalisation and the final averages
+    for kept in ("call ReadParameters", "call CheckPoint(trap,Path,xend,isopen,iworm)", "end program vpi"):
+        assert kept in gen, kept
+    # every procedure the generated driver calls is declared in the bind(C) module
+    mod = open(os.path.join(root, "fortran", "pigs_cuda_mod.f90")).read().lower()
+    import re
+    for name in set(re.findall(r"\b(pigs_[a-z_]+)\(", gen)):
+        assert f"function {name}" in mod, name
