@@ -259,3 +259,25 @@ def test_fortran_driver_generator_applies_all_five_edits():
     import re
     for name in set(re.findall(r"\b(pigs_[a-z_]+)\(", gen)):
         assert f"function {name}" in mod, name
+
+
+def test_fortran_bind_c_types_match_the_c_structs():
+    """fortran/pigs_cuda_mod.f90 cannot be compiled here, so its two interoperable types are checked field by field
+    (name, order, element size, array length) against the ctypes mirror of include/pigs_cuda.h"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "fortran", "pigs_cuda_mod.f90")).read()
+    size = {"c_int32_t": 4, "c_int": 4, "c_int64_t": 8, "c_double": 8}
+    for tname, struct in (("pigs_params", PigsParams), ("pigs_block_result", PigsBlockResult)):
+        body = re.search(rf"type, bind\(C\) :: {tname}\n(.*?)end type {tname}", src, re.S).group(1)
+        fields = []
+        for line in body.splitlines():
+            line = line.split("!")[0].strip()
+            if not line:
+                continue
+            m = re.match(r"(?:integer|real)\((\w+)\)\s*::\s*(.*)", line)
+            assert m, line
+            for item in re.findall(r"(\w+)(?:\((\d+)\))?", m.group(2)):
+                fields.append((item[0].lower(), size[m.group(1)], int(item[1] or 1)))
+        want = [(n.lower(), C.sizeof(t) // (t._length_ if hasattr(t, "_length_") else 1), t._length_ if hasattr(t, "_length_") else 1)
+                for n, t in struct._fields_]
+        assert fields == want, (tname, [a for a, b in zip(fields, want) if a != b][:3])
