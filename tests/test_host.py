@@ -281,3 +281,20 @@ def test_fortran_bind_c_types_match_the_c_structs():
         want = [(n.lower(), C.sizeof(t) // (t._length_ if hasattr(t, "_length_") else 1), t._length_ if hasattr(t, "_length_") else 1)
                 for n, t in struct._fields_]
         assert fields == want, (tname, [a for a, b in zip(fields, want) if a != b][:3])
+
+
+def test_fortran_interfaces_have_the_c_prototypes_arity():
+    """every interface of fortran/pigs_cuda_mod.f90 names a function include/pigs_cuda.h declares, with as many arguments"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mod = open(os.path.join(root, "fortran", "pigs_cuda_mod.f90")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", open(os.path.join(root, "include", "pigs_cuda.h")).read(), flags=re.S)
+    protos = {m.group(1): (0 if m.group(2).strip() in ("", "void") else m.group(2).count(",") + 1)
+              for m in re.finditer(r"\b(pigs_\w+)\s*\(([^()]*)\)\s*;", hdr)}
+    seen = 0
+    for m in re.finditer(r"function\s+(pigs_\w+)\s*\(([^)]*)\)\s*(?:&\s*\n\s*)?bind\(C,\s*name='(\w+)'\)", mod, flags=re.I):
+        name, args, cname = m.group(1), m.group(2), m.group(3)
+        assert name == cname and cname in protos, cname
+        nargs = len([a for a in re.sub(r"&\s*\n\s*", "", args).split(",") if a.strip()])
+        assert nargs == protos[cname], (cname, nargs, protos[cname])
+        seen += 1
+    assert seen >= 20
