@@ -155,6 +155,23 @@ allv = rng.integers(0, 1000, size=(10, 50)).astype(np.float64)
 mine = allv[first:first + count].sum(axis=0)
 red = allreduce_vector_host(mine)
 assert np.array_equal(red, allv.sum(axis=0)), (rank, red[:4])
+# the same with real chains: global chain c runs the reference's stream seed + c whatever rank owns it, so the
+# all-reduced block sums of a 2-rank run equal those of the 1-rank run (the oracle stands in for the GPU backend)
+from tests.common import CW, oracle_cfg
+from oracle.pigs_oracle import Oracle
+KEYS = ("sumE", "sumEt", "sumV", "idiag_block", "try_stag", "acc_bd", "acc_head", "acc_tail", "try_open", "acc_open")
+def chain_block(c):
+    o = Oracle(oracle_cfg(dict(CW, seed=CW["seed"] + c)))
+    o.fill_tables()
+    o.init()
+    b = o.run_block(4)[0]
+    return np.array([float(b[k]) for k in KEYS] + [float(x) for x in b["bead_updates"]])
+nch = 5
+first, count = shard_chains(nch, rank, world)
+mine = np.sum([chain_block(c) for c in range(first, first + count)], axis=0)
+red = allreduce_vector_host(mine)
+serial = np.sum([chain_block(c) for c in range(nch)], axis=0)
+assert np.allclose(red, serial, rtol=1e-13, atol=0) and np.array_equal(red[3:], serial[3:]), (rank, red, serial)
 dist.barrier()
 if rank == 0:
     print("GLOO_OK", world)
